@@ -1,0 +1,115 @@
+/*
+ * nerf_b200.h -- C-ABI of the B200-native vanilla-NeRF volume-rendering hot path.
+ *
+ * Drop-in boundary.  The reference (nerficg) has no FFI for this path: every
+ * stage is a chain of ATen ops issued from Python.  Each entry point below replaces the ATen
+ * chain of one reference function; the reference-side binding is the ctypes stub shown in
+ * INTEGRATION.md (nerficg_b200/_lib.py is the real one).  Citations are relative to the
+ * reference checkout (/root/reference).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; plain C types only.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, allocates
+ *     nothing, creates no threads or streams, and is re-entrant per device.
+ *   - return value 0 = success; negative = error, message via nerf_last_error().
+ *   - sm_100 only: there is no CPU path and no fallback (nerf_device_check()).
+ *   - "samples" of a pass are ordered ray-major: sample e = ray * S + i.
+ *   - an MLP output is packed as float4 (r, g, b, sigma) per sample ("rgbsigma").
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_ABI_VERSION 1
+
+/* fixed architecture handled by the CUDA path (configs/nerf_lego.yaml MODEL section,
+ * src/Methods/NeRF/Model.py:86-96): 8 layers x 256, skip before layer 5, 1 colour layer,
+ * L=10 / L=4 frequencies, input appended, ReLU.  Anything else is rejected by the host. */
+#define NERF_N_PARAM_TENSORS 24
+#define NERF_TILE 128 /* samples per MMA tile */
+
+int nerf_abi_version(void);
+const char* nerf_last_error(void);
+/* 0 if `device` is an sm_100 GPU, negative otherwise (no fallback path exists). */
+int nerf_device_check(int device);
+
+/* ---- parameter layout ---------------------------------------------------------------
+ * One NeRFBlock (src/Methods/NeRF/Model.py:35-54) is a flat fp32 buffer; tensor t of the
+ * torch registration order (initial_layers.{0..7}.0.{weight,bias}, feature_layer.*,
+ * density_layer.*, color_layers.0.*, color_layers.2.*) starts at offsets[t] floats and
+ * keeps torch's row-major (out, in) layout.  Starts are padded to 4 floats. */
+int nerf_param_layout(int64_t* offsets /*[24]*/, int64_t* sizes /*[24]*/, int64_t* total);
+
+/* ---- K1: stratified sampling -- generate_samples, src/Methods/NeRF/utils.py:57-75 ----
+ * z[n_rays][n_samples]; u = uniform noise of the same shape (torch.rand) or NULL for the
+ * deterministic linspace. */
+int nerf_sample_stratified(float* z, const float* u, int n_rays, int n_samples, float near_plane, float far_plane,
+                           void* stream);
+
+/* ---- K2: inverse-CDF importance sampling + merge -------------------------------------
+ * generate_samples_from_pdf (src/Methods/NeRF/utils.py:78-109) followed by
+ * sort(cat(z_coarse, z_fine)) (src/Methods/NeRF/Renderer.py:70).
+ * z_coarse, w_coarse: [n_rays][n_coarse]; u: [n_rays][n_fine] or NULL (linspace(0,1,n_fine));
+ * z_merged: [n_rays][n_coarse+n_fine] ascending; z_fine (optional, may be NULL): the
+ * unsorted fine samples, exported for stage parity tests. */
+int nerf_sample_importance(float* z_merged, float* z_fine, const float* z_coarse, const float* w_coarse, const float* u,
+                           int n_rays, int n_coarse, int n_fine, void* stream);
+
+/* ---- K5: alpha compositing forward -- integrate_samples, src/Methods/NeRF/utils.py:112-136
+ * z [n][S], rgbsigma [n][S][4], dirs [n][3] (un-normalised), background [3] or NULL.
+ * Outputs rgb [n][3], depth [n], alpha [n], weights [n][S] (NULL to skip). */
+int nerf_composite_forward(float* rgb, float* depth, float* alpha, float* weights, const float* z,
+                           const float* rgbsigma, const float* dirs, const float* background, int n_rays, int n_samples,
+                           void* stream);
+
+/* ---- K6: alpha compositing backward (autograd of integrate_samples) ----
+ * Upstream grads g_rgb [n][3] (required), g_depth [n], g_alpha [n] (NULL = zero).
+ * d_rgbsigma [n][S][4] receives (dL/dr, dL/dg, dL/db, dL/dsigma) times grad_scale.
+ * relu_mask != 0 zeroes dL/dsigma where sigma <= 0 (folds the density ReLU of
+ * src/Methods/NeRF/Model.py:77 so the 1e10 last-interval term never leaves fp32). */
+int nerf_composite_backward(float* d_rgbsigma, const float* z, const float* rgbsigma, const float* dirs,
+                            const float* background, const float* g_rgb, const float* g_depth, const float* g_alpha,
+                            int n_rays, int n_samples, int relu_mask, float grad_scale, void* stream);
+
+/* ---- weight images for the tensor-core MLP ---------------------------------------------
+ * Converts one block's flat fp32 parameters into fp16 forward and fp16 transposed
+ * (backward) UMMA operand images (128B-swizzled K-major panels).  `packed` needs
+ * nerf_mlp_packed_bytes() bytes, 1024-byte aligned. */
+size_t nerf_mlp_packed_bytes(void);
+int nerf_mlp_pack(void* packed, const float* params, int with_backward, void* stream);
+
+/* ---- K3: fused encoding + MLP forward -- FrequencyEncoding + NeRFBlock.forward ---------
+ * (src/Methods/NeRF/utils.py:32-36, src/Methods/NeRF/Model.py:59-83) applied to the
+ * sample positions origins + dirs * z (src/Methods/NeRF/Renderer.py:54,75).
+ * origins/dirs/viewdirs [n_rays][3], z [n_rays][S], noise [n_rays*S] already scaled by the
+ * noise std, or NULL.  rgbsigma [n_rays*S][4].  `stash` (NULL for inference) receives the
+ * activations the backward needs; it needs nerf_mlp_stash_bytes(n_rays*S) bytes, 1024-aligned. */
+size_t nerf_mlp_stash_bytes(int64_t n_samples);
+int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed, const float* params, const float* origins,
+                     const float* dirs, const float* viewdirs, const float* z, const float* noise, int n_rays,
+                     int n_samples, void* stream);
+
+/* ---- K4: MLP backward (autograd of NeRFBlock.forward w.r.t. its parameters) ------------
+ * d_rgbsigma [n_rays*S][4] = grad_scale * dL/d(r,g,b,sigma_raw) (from K6 with relu_mask=1).
+ * Gradients are ACCUMULATED into `grads` (flat fp32, layout of nerf_param_layout) after
+ * division by grad_scale.  `workspace` needs nerf_mlp_backward_workspace_bytes(n) bytes. */
+size_t nerf_mlp_backward_workspace_bytes(int64_t n_samples);
+int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                      const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
+                      void* stream);
+
+/* ---- self test of the tcgen05 building blocks (used by tests/ only) --------------------
+ * D[128][n] = A[128][k] * B[n][k]^T with operand images built on device; mode selects the
+ * descriptor flavour (0: K-major fp16, 1: MN-major operands as in wgrad, 2: K-major bf16). */
+int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,444 @@
+// mlp_fwd.cu -- K3: positional encoding + the 8x256 skip-connected NeRF MLP as ONE fused,
+// persistent, warp-specialised tcgen05 kernel.
+//
+// A CTA owns one SM and walks pairs of 128-sample tiles ("slots" 0/1) through the whole 10-stage
+// chain (mlp_layout.cuh) without touching HBM in between:
+//   warp 0      weight producer: streams fp16 weight panels (pre-swizzled UMMA images) from L2
+//               into a shared-memory ring with 1-D bulk copies (TMA engine) + mbarriers
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) from the
+//               slot's activation panels (A, shared memory) and the ring (B); accumulators live
+//               in TMEM (2 slots x 256 fp32 columns = all 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue of slot 0 \  tcgen05.ld accumulator -> +bias, ReLU -> fp16 -> swizzled
+//   warps 8-11  epilogue of slot 1 /  A-operand panels of the next stage (in place); the two slots
+//               ping-pong so one slot's epilogue overlaps the other slot's MMAs.
+// The density head (256->1) and the RGB head (128->3, sigmoid) are evaluated on CUDA cores inside
+// the epilogues of stages 7 and 9, so the kernel emits packed (r,g,b,sigma) per sample.
+// Training additionally stashes every operand image the backward needs (bulk stores from shared
+// memory, region-major, see mlp_layout.cuh) and per-layer ReLU bit masks.
+#include "common.cuh"
+#include "mlp_layout.cuh"
+#include "tc.cuh"
+#include "../../include/nerf_b200.h"
+
+namespace nerf {
+using namespace tc;
+
+namespace fwd {
+constexpr int kThreads = 384;
+constexpr int kRingStages = 2;
+constexpr uint32_t kRingStageBytes = kPanelBytes256;
+// shared memory map (offsets from the 1024-aligned base)
+constexpr uint32_t kSlotBytes = kActBytes + kPanelBytes128;  // act (4 panels) + enc (1 panel)
+constexpr uint32_t kOffRing = 2 * kSlotBytes;
+constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
+constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;  // + barriers + alignment slack
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+}  // namespace fwd
+
+struct FwdParams {
+  float4* rgbsigma;
+  uint8_t* stash;  // nullptr for inference
+  const uint8_t* packed;
+  const float* params;
+  const float* origins;
+  const float* dirs;
+  const float* viewdirs;
+  const float* z;
+  const float* noise;
+  int n_rays;
+  int n_samples;    // S
+  int64_t n_evals;  // n_rays * S
+  int n_tiles;
+};
+
+// ---- per-row input encoding ----------------------------------------------------------------
+// 63 position features [x, cos(2^k x_i), sin(2^k x_i)] (reference utils.py:32-36) as 64 halves.
+// sin/cos of 2^k x are produced by exact sincosf at k = 0 and k = 5 plus double-angle steps
+// (<= 4 doublings: error <= 16 ulp, far below the fp16 operand rounding).
+__device__ __forceinline__ void encode_axis(float v, int n_freq, float* cs_out /* [2*n_freq]: cos block, sin block */) {
+  float s, c;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if (k >= n_freq) break;
+    if (k == 0 || k == 5) {
+      sincosf(v * (float)(1 << k), &s, &c);
+    } else {
+      const float s2 = 2.f * s * c;
+      const float c2 = 1.f - 2.f * s * s;
+      s = s2;
+      c = c2;
+    }
+    cs_out[k] = c;
+    cs_out[n_freq + k] = s;
+  }
+}
+
+__device__ __forceinline__ void write_row_panel(uint32_t panel_smem, int row, const float* vals /*[64]*/) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    st_shared_v4(panel_smem + panel_chunk_offset(row, ch), pack_half2(vals[8 * ch + 0], vals[8 * ch + 1]),
+                 pack_half2(vals[8 * ch + 2], vals[8 * ch + 3]), pack_half2(vals[8 * ch + 4], vals[8 * ch + 5]),
+                 pack_half2(vals[8 * ch + 6], vals[8 * ch + 7]));
+  }
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
+  using namespace fwd;
+  using L = ParamLayout;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + kOffBars;
+  // barrier map (8 bytes each)
+  const uint32_t bar_w_full = bars;                       // [kRingStages]
+  const uint32_t bar_w_empty = bars + 8 * kRingStages;    // [kRingStages]
+  const uint32_t bar_a_ready = bars + 16 * kRingStages;   // [2] operand of the next stage written + accumulator drained
+  const uint32_t bar_acc_ready = bar_a_ready + 16;        // [2] accumulator complete
+  const uint32_t tmem_slot = bar_acc_ready + 16;          // uint32: TMEM base address
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingStages; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_a_ready + 8 * s, 128);
+      mbar_init(bar_acc_ready + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int pairs_total = (p.n_tiles + 1) / 2;
+  const int n_iters = (pairs_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        for (int st = 0; st < kFwdStages; ++st) {
+          for (int slot = 0; slot < 2; ++slot) {
+            if (tile_of(it, slot) >= p.n_tiles) continue;
+            const int first = fwd_first_panel(st), np = fwd_panels(st);
+            for (int pp = 0; pp < np; ++pp) {
+              mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+              const uint32_t bytes = fwd_panel_bytes(first + pp);
+              mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
+              bulk_g2s(smem_base + kOffRing + stage * kRingStageBytes, p.packed + fwd_panel_offset(first + pp), bytes,
+                       bar_w_full + 8 * stage);
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_phase[2] = {0, 0};
+      constexpr uint32_t idesc256 = make_idesc(128, 256, kF16, kF16, 0, 0);
+      constexpr uint32_t idesc128 = make_idesc(128, 128, kF16, kF16, 0, 0);
+      for (int it = 0; it < n_iters; ++it) {
+        for (int st = 0; st < kFwdStages; ++st) {
+          for (int slot = 0; slot < 2; ++slot) {
+            if (tile_of(it, slot) >= p.n_tiles) continue;
+            const uint32_t act = smem_base + slot * kSlotBytes;
+            const uint32_t enc = act + kActBytes;
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]);
+            a_phase[slot] ^= 1;
+            tc_fence_after();
+            const int np = fwd_panels(st);
+            uint32_t accumulate = 0;
+            for (int pp = 0; pp < np; ++pp) {
+              // A operand: stage 0 reads the encoding panel; panel 4 of stages 5 / 9 is the encoding / direction panel
+              const uint32_t a_panel = (st == 0 || pp == 4) ? enc : act + pp * kPanelBytes128;
+              const int ksteps = (st == 9 && pp == 4) ? 2 : 4;
+              mbar_wait(bar_w_full + 8 * stage, phase);
+              tc_fence_after();
+              const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                umma(d_tmem, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), st == 9 ? idesc128 : idesc256, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(bar_w_empty + 8 * stage);
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            umma_commit(bar_acc_ready + 8 * slot);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue warpgroups ===============================
+    const int slot = (warp - 4) >> 2;
+    const int wq = warp & 3;                 // TMEM lane quarter of this warp
+    const int row = wq * 32 + lane;          // row of the tile owned by this thread
+    const int tg = threadIdx.x - 128 - slot * 128;  // 0..127 within the warpgroup
+    const uint32_t act = smem_base + slot * kSlotBytes;
+    const uint32_t enc = act + kActBytes;
+    const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t bar_id = 1 + slot;  // named barrier of this warpgroup
+    uint32_t acc_phase = 0;
+    const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile = tile_of(it, slot);
+      if (tile >= p.n_tiles) break;
+      const int64_t e = (int64_t)tile * kTile + row;  // sample index
+      const bool valid = e < p.n_evals;
+      const int ray = valid ? (int)(e / p.n_samples) : 0;
+
+      // stash helper: one thread bulk-stores an image from shared memory after the group fenced its writes
+      auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {
+        if (kTrain) {
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (tg == 0) {
+            bulk_s2g(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes);
+            bulk_commit();
+          }
+        }
+      };
+      // before overwriting a buffer that may still be read by an in-flight bulk store
+      auto stash_drain = [&]() {
+        if (kTrain) {
+          if (tg == 0) bulk_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+        }
+      };
+
+      // ---------------- prologue: position encoding -> enc panel ----------------
+      float vdx = 0.f, vdy = 0.f, vdz = 0.f;
+      {
+        float vals[64];
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (valid) {
+          const float zz = __ldg(p.z + e);
+          x0 = __fadd_rn(__ldg(p.origins + 3 * ray + 0), __fmul_rn(__ldg(p.dirs + 3 * ray + 0), zz));
+          x1 = __fadd_rn(__ldg(p.origins + 3 * ray + 1), __fmul_rn(__ldg(p.dirs + 3 * ray + 1), zz));
+          x2 = __fadd_rn(__ldg(p.origins + 3 * ray + 2), __fmul_rn(__ldg(p.dirs + 3 * ray + 2), zz));
+          vdx = __ldg(p.viewdirs + 3 * ray + 0);
+          vdy = __ldg(p.viewdirs + 3 * ray + 1);
+          vdz = __ldg(p.viewdirs + 3 * ray + 2);
+        }
+        vals[0] = x0;
+        vals[1] = x1;
+        vals[2] = x2;
+        encode_axis(x0, 10, vals + 3);
+        encode_axis(x1, 10, vals + 23);
+        encode_axis(x2, 10, vals + 43);
+        vals[63] = 0.f;
+        stash_drain();  // previous tile's DIR / G stores still reading enc / act
+        write_row_panel(enc, row, vals);
+      }
+      stash_store(kStashEnc, enc, kPanelBytes128);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_a_ready + 8 * slot);
+
+      float sigma = 0.f;
+      // ---------------- chain stages ----------------
+#pragma unroll 1
+      for (int st = 0; st < kFwdStages; ++st) {
+        mbar_wait(bar_acc_ready + 8 * slot, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (st < 9) {
+          // hidden layers 0..7 (ReLU) and the feature layer (stage 8, linear)
+          const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF);
+          const bool relu = st < 8;
+          float dens = 0.f;
+          uint32_t* mask_dst = nullptr;
+          if (kTrain && relu)
+            mask_dst = reinterpret_cast<uint32_t*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
+                                                   (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
+          stash_drain();  // the act image of the previous stage may still be being stored
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + c0, v);
+            float bv[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
+              bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
+            }
+            tmem_ld_wait();
+            float h[32];
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]) + bv[j];
+              if (relu) {
+                m |= (x > 0.f ? 1u : 0u) << j;
+                x = fmaxf(x, 0.f);
+              }
+              h[j] = x;
+            }
+            if (kTrain && relu) mask_dst[c0 >> 5] = m;
+            if (st == 7) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWS + c0) + q);
+                dens = fmaf(h[4 * q], w4.x, dens);
+                dens = fmaf(h[4 * q + 1], w4.y, dens);
+                dens = fmaf(h[4 * q + 2], w4.z, dens);
+                dens = fmaf(h[4 * q + 3], w4.w, dens);
+              }
+            }
+            const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(h[8 * q], h[8 * q + 1]),
+                           pack_half2(h[8 * q + 2], h[8 * q + 3]), pack_half2(h[8 * q + 4], h[8 * q + 5]),
+                           pack_half2(h[8 * q + 6], h[8 * q + 7]));
+            }
+          }
+          if (st == 7) {
+            float raw = dens + __ldg(p.params + L::kBS);
+            if (p.noise != nullptr && valid) raw += __ldg(p.noise + e);
+            sigma = fmaxf(raw, 0.f);
+          }
+          if (st == 8) {
+            // direction encoding -> enc panel (the x encoding was last read by stage 5)
+            float vals[64];
+            vals[0] = vdx;
+            vals[1] = vdy;
+            vals[2] = vdz;
+            encode_axis(vdx, 4, vals + 3);
+            encode_axis(vdy, 4, vals + 11);
+            encode_axis(vdz, 4, vals + 19);
+#pragma unroll
+            for (int j = 27; j < 64; ++j) vals[j] = 0.f;
+            write_row_panel(enc, row, vals);
+            stash_store(kStashDir, enc, kPanelBytes128);
+          }
+          stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_a_ready + 8 * slot);
+        } else {
+          // stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores
+          float a0 = __ldg(p.params + L::kBC1 + 0), a1 = __ldg(p.params + L::kBC1 + 1), a2 = __ldg(p.params + L::kBC1 + 2);
+          stash_drain();  // the F image store reads act, which receives g below
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + c0, v);
+            tmem_ld_wait();
+            float g[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kBC0 + c0) + q);
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
+              g[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
+              g[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
+              g[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
+              g[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
+              a0 = fmaf(g[4 * q + 0], w0.x, fmaf(g[4 * q + 1], w0.y, fmaf(g[4 * q + 2], w0.z, fmaf(g[4 * q + 3], w0.w, a0))));
+              a1 = fmaf(g[4 * q + 0], w1.x, fmaf(g[4 * q + 1], w1.y, fmaf(g[4 * q + 2], w1.z, fmaf(g[4 * q + 3], w1.w, a1))));
+              a2 = fmaf(g[4 * q + 0], w2.x, fmaf(g[4 * q + 1], w2.y, fmaf(g[4 * q + 2], w2.z, fmaf(g[4 * q + 3], w2.w, a2))));
+            }
+            if (kTrain) {
+              const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(g[8 * q], g[8 * q + 1]),
+                             pack_half2(g[8 * q + 2], g[8 * q + 3]), pack_half2(g[8 * q + 4], g[8 * q + 5]),
+                             pack_half2(g[8 * q + 6], g[8 * q + 7]));
+              }
+            }
+          }
+          stash_store(kStashG, act, 2 * kPanelBytes128);
+          if (valid) {
+            float4 o;
+            o.x = 1.f / (1.f + expf(-a0));
+            o.y = 1.f / (1.f + expf(-a1));
+            o.z = 1.f / (1.f + expf(-a2));
+            o.w = sigma;
+            p.rgbsigma[e] = o;
+          }
+          // the accumulator has been drained; the arrive that releases it is the next tile's prologue
+          tc_fence_before();
+        }
+      }
+    }
+    if (kTrain && tg == 0) bulk_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace nerf
+
+extern "C" size_t nerf_mlp_stash_bytes(int64_t n_samples) {
+  const uint64_t n_tiles = (uint64_t)((n_samples + nerf::kTile - 1) / nerf::kTile);
+  return (size_t)(nerf::stash_tile_bytes_total() * n_tiles);
+}
+
+extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed, const float* params, const float* origins,
+                                const float* dirs, const float* viewdirs, const float* z, const float* noise, int n_rays,
+                                int n_samples, void* stream) {
+  using namespace nerf;
+  if (n_rays <= 0) return 0;
+  NERF_CHECK_ARG(rgbsigma && packed && params && origins && dirs && viewdirs && z, "mlp_forward: null pointer");
+  NERF_CHECK_ARG(n_samples >= 1, "mlp_forward: n_samples must be >= 1");
+  const int64_t n_evals = (int64_t)n_rays * n_samples;
+  NERF_CHECK_ARG(n_evals < (int64_t(1) << 31) - kTile, "mlp_forward: n_rays*n_samples must be < 2^31 per call");
+  NERF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0,
+                 "mlp_forward: packed must be 128-byte and rgbsigma 16-byte aligned");
+  NERF_CHECK_ARG(stash == nullptr || (reinterpret_cast<uintptr_t>(stash) & 127) == 0, "mlp_forward: stash must be 128-byte aligned");
+  FwdParams p;
+  p.rgbsigma = reinterpret_cast<float4*>(rgbsigma);
+  p.stash = static_cast<uint8_t*>(stash);
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.params = params;
+  p.origins = origins;
+  p.dirs = dirs;
+  p.viewdirs = viewdirs;
+  p.z = z;
+  p.noise = noise;
+  p.n_rays = n_rays;
+  p.n_samples = n_samples;
+  p.n_evals = n_evals;
+  p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
+  const int pairs = (p.n_tiles + 1) / 2;
+  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
+    NERF_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "mlp_forward: cudaFuncSetAttribute failed: %s",
+                   cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    attr_set = true;
+  }
+  if (stash != nullptr)
+    mlp_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    mlp_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+  NERF_CHECK_LAUNCH("mlp_fwd_kernel");
+  return 0;
+}

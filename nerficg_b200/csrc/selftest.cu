@@ -1,0 +1,120 @@
+// selftest.cu -- one-tile exerciser of the tcgen05 building blocks in tc.cuh.
+// D[128][n] = A[128][k] * B[n][k]^T, operands converted on device into the panel format.
+// mode 0: fp16 x fp16, K-major panels (forward / dgrad flavour)
+// mode 1: fp16 x fp16, MN-major view of reduction-major panels (wgrad flavour)
+// mode 2: bf16 x bf16, K-major.  (Mixed bf16 x fp16 operands are an illegal instruction on sm_100a --
+// measured in round 1 -- which is why the backward uses loss-scaled fp16 gradients.)
+#include "common.cuh"
+#include "tc.cuh"
+#include "../../include/nerf_b200.h"
+
+namespace nerf {
+using namespace tc;
+
+__device__ __forceinline__ uint16_t to_bits(float v, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128, 1) selftest_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                          const float* __restrict__ b, int n, int k, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const bool mn_major = (mode == 1);
+  const bool a_bf16 = (mode == 2);
+  const uint32_t a_bytes = 128u * k * 2u;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + a_bytes;
+  const int tid = threadIdx.x;
+
+  if (!mn_major) {
+    // K-major: panel p holds columns [64p, 64p+64) of every row; A panels have 128 rows, B panels n rows
+    for (int i = tid; i < 128 * k; i += 128) {
+      int r = i / k, c = i % k;
+      *reinterpret_cast<uint16_t*>(sa + (c / 64) * (128 * 128) + panel_offset(r, c % 64)) = to_bits(a[i], a_bf16);
+    }
+    for (int i = tid; i < n * k; i += 128) {
+      int r = i / k, c = i % k;
+      *reinterpret_cast<uint16_t*>(sb + (c / 64) * (n * 128) + panel_offset(r, c % 64)) = to_bits(b[i], a_bf16);
+    }
+  } else {
+    // reduction-major: panel g holds M/N indices [64g, 64g+64) as columns, rows = k index
+    for (int i = tid; i < 128 * k; i += 128) {
+      int m = i / k, kk = i % k;
+      *reinterpret_cast<uint16_t*>(sa + (m / 64) * (k * 128) + panel_offset(kk, m % 64)) = to_bits(a[i], a_bf16);
+    }
+    for (int i = tid; i < n * k; i += 128) {
+      int nn = i / k, kk = i % k;
+      *reinterpret_cast<uint16_t*>(sb + (nn / 64) * (k * 128) + panel_offset(kk, nn % 64)) = to_bits(b[i], a_bf16);
+    }
+  }
+  uint32_t ncols = 32;
+  while (ncols < static_cast<uint32_t>(n)) ncols <<= 1;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) {
+    tmem_alloc(smem_u32(&tmem_base_s), ncols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, n, a_bf16 ? kBF16 : kF16, a_bf16 ? kBF16 : kF16, mn_major ? 1 : 0, mn_major ? 1 : 0);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < k / 16; ++ks) {
+      uint64_t da, db;
+      if (!mn_major) {
+        da = desc_kmajor(smem_u32(sa) + (ks / 4) * (128 * 128), ks % 4);
+        db = desc_kmajor(smem_u32(sb) + (ks / 4) * (n * 128), ks % 4);
+      } else {
+        da = desc_mnmajor(smem_u32(sa), ks, k * 128);
+        db = desc_mnmajor(smem_u32(sb), ks, k * 128);
+      }
+      umma(tmem, da, db, idesc, acc);
+      acc = 1;
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int warp = tid / 32, lane = tid % 32;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < n) out[row * n + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace nerf
+
+extern "C" int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(n >= 32 && n <= 256 && n % 32 == 0, "selftest: n must be a multiple of 32 in [32,256], got %d", n);
+  NERF_CHECK_ARG(k >= 64 && k <= 256 && k % 64 == 0, "selftest: k must be a multiple of 64 in [64,256], got %d", k);
+  NERF_CHECK_ARG(mode >= 0 && mode <= 2, "selftest: bad mode %d", mode);
+  size_t smem = 1024 + size_t(128) * k * 2 + size_t(n) * k * 2;
+  cudaError_t e = cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  NERF_CHECK_ARG(e == cudaSuccess, "selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k, mode);
+  NERF_CHECK_LAUNCH("selftest_kernel");
+  return 0;
+}
