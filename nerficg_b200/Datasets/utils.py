@@ -1,0 +1,150 @@
+"""Ray/data model of the NeRF path (reference src/Datasets/utils.py: RayBatch :536-670, RayCollection
+:673-690, View.get_rays :1053-1074, apply_background_color :185-189).  Field names and semantics are the
+reference's; everything unrelated to the vanilla-NeRF path (point clouds, flow IO, pose PCA) is absent."""
+from __future__ import annotations
+
+from dataclasses import dataclass, fields
+
+import numpy as np
+import torch
+
+from .. import Framework
+from ..Cameras.Perspective import PerspectiveCamera
+
+
+@dataclass(frozen=True)
+class RayBatch:
+    """Per-ray tensors, all (n, C) with identical n, dtype and device."""
+    origin: torch.Tensor
+    direction: torch.Tensor
+    view_direction: torch.Tensor | None = None
+    rgb: torch.Tensor | None = None
+    alpha: torch.Tensor | None = None
+    depth: torch.Tensor | None = None
+    timestamp: torch.Tensor | None = None
+    _skip_post_init: bool = False
+
+    _FIELDS = ('origin', 'direction', 'view_direction', 'rgb', 'alpha', 'depth', 'timestamp')
+
+    def __post_init__(self):
+        if self._skip_post_init:
+            return
+        n, dtype, device = self.origin.shape[0], self.origin.dtype, self.origin.device
+        for member in fields(self):
+            value = getattr(self, member.name)
+            if isinstance(value, torch.Tensor):
+                if value.shape[0] != n:
+                    raise Framework.DatasetError(f'{member.name} has {value.shape[0]} rays, origin has {n}')
+                if value.dtype != dtype:
+                    raise Framework.DatasetError(f'{member.name} is {value.dtype}, origin is {dtype}')
+                if value.device != device:
+                    raise Framework.DatasetError(f'{member.name} is on {value.device}, origin is on {device}')
+
+    def __len__(self) -> int:
+        return self.origin.shape[0]
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.origin.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self.origin.device
+
+    def _map(self, fn) -> 'RayBatch':
+        return RayBatch(**{k: (None if getattr(self, k) is None else fn(getattr(self, k))) for k in self._FIELDS},
+                        _skip_post_init=True)
+
+    def __getitem__(self, idx) -> 'RayBatch':
+        if idx is Ellipsis or (isinstance(idx, slice) and idx == slice(None)):
+            return self
+        if isinstance(idx, int):
+            idx = slice(idx, idx + 1)
+        return self._map(lambda t: t[idx])
+
+    def to(self, dtype: torch.dtype = None, device: torch.device = None, non_blocking: bool = False) -> 'RayBatch':
+        if (dtype is None or dtype == self.dtype) and (device is None or torch.device(device) == self.device):
+            return self
+        return self._map(lambda t: t.to(dtype=dtype, device=device, non_blocking=non_blocking))
+
+    def cpu(self) -> 'RayBatch':
+        return self.to(device=torch.device('cpu'))
+
+    def cuda(self, non_blocking: bool = False) -> 'RayBatch':
+        return self.to(device=Framework.config.GLOBAL.DEFAULT_DEVICE, non_blocking=non_blocking)
+
+    def split(self, chunk_size: int) -> list['RayBatch']:
+        return [self[i:i + chunk_size] for i in range(0, len(self), chunk_size)]
+
+    @classmethod
+    def cat(cls, batches: list['RayBatch']) -> 'RayBatch':
+        if not batches:
+            raise Framework.DatasetError('no RayBatch instances to concatenate')
+        out = {}
+        for k in cls._FIELDS:
+            present = [getattr(b, k) is not None for b in batches]
+            if any(present) and not all(present):
+                raise Framework.DatasetError(f'RayBatch field "{k}" is not present in some batches')
+            out[k] = torch.cat([getattr(b, k) for b in batches], dim=0) if all(present) else None
+        return cls(**out, _skip_post_init=True)
+
+
+@dataclass(frozen=True)
+class RayCollection:
+    """All rays of a subset with one slice per view."""
+    rays: RayBatch
+    camera_slices: list
+
+    def __len__(self) -> int:
+        return len(self.rays)
+
+    def __getitem__(self, index: int) -> RayBatch:
+        return self.rays[self.camera_slices[index]]
+
+    @property
+    def all_rays(self) -> RayBatch:
+        return self.rays
+
+
+def apply_background_color(raw_rgb: torch.Tensor, alpha: torch.Tensor, background_color: torch.Tensor,
+                           is_chw: bool = True) -> torch.Tensor:
+    """clamp(lerp(bg, rgb, alpha), 0, 1)."""
+    if is_chw:
+        background_color = background_color[:, None, None]
+    return torch.lerp(background_color.to(raw_rgb.device).expand_as(raw_rgb), raw_rgb, alpha).clamp(0, 1)
+
+
+class View:
+    """A posed camera with optional image annotations (rgb 3xHxW, alpha 1xHxW, depth 1xHxW).
+
+    ``c2w`` is a 4x4 (or 3x4) camera-to-world matrix whose rotation columns are the camera's x (right),
+    y (down) and z (forward) axes in world space."""
+
+    def __init__(self, camera: PerspectiveCamera, c2w: np.ndarray | torch.Tensor, rgb: torch.Tensor | None = None,
+                 alpha: torch.Tensor | None = None, depth: torch.Tensor | None = None, timestamp: float = 0.0,
+                 frame_idx: int = 0) -> None:
+        self.camera = camera
+        self.c2w = torch.as_tensor(np.asarray(c2w), dtype=torch.float32)
+        self.rgb, self.alpha, self.depth = rgb, alpha, depth
+        self.timestamp = timestamp
+        self.frame_idx = frame_idx
+
+    @property
+    def position(self) -> torch.Tensor:
+        return self.c2w[:3, 3]
+
+    @property
+    def rotation(self) -> torch.Tensor:
+        return self.c2w[:3, :3]
+
+    def get_rays(self) -> RayBatch:
+        """Rays of every pixel (row-major) on the default CUDA device."""
+        device = Framework.config.GLOBAL.DEFAULT_DEVICE
+        local = self.camera.compute_local_ray_directions(device=device)
+        direction = local @ self.rotation.to(device).T
+        origin = self.position.to(device).expand_as(direction)
+        flat = lambda img: None if img is None else img.to(device).permute(1, 2, 0).reshape(direction.shape[0], -1)
+        ts = torch.full((direction.shape[0], 1), float(self.timestamp), dtype=torch.float32, device=device)
+        return RayBatch(origin=origin.contiguous(), direction=direction.contiguous(),
+                        view_direction=torch.nn.functional.normalize(direction, dim=-1),
+                        rgb=flat(self.rgb), alpha=flat(self.alpha), depth=flat(self.depth), timestamp=ts)

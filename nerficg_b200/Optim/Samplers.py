@@ -1,0 +1,73 @@
+"""Ray-batch samplers of the trainer (reference src/Optim/Samplers/{DatasetSamplers,ImageSamplers,utils}.py)."""
+from __future__ import annotations
+
+import torch
+
+from .. import Framework
+
+
+class RandomImageSampler:
+    """Uniform random pixel ids with replacement (ImageSamplers.py:42-45); drawn on the CPU generator like the reference."""
+
+    def __init__(self, num_elements: int) -> None:
+        self.num_elements = num_elements
+
+    def get(self, ray_batch_size: int) -> torch.Tensor:
+        return torch.randint(low=0, high=self.num_elements, size=(ray_batch_size,))
+
+
+class RandomSequentialSampler:
+    """Random permutation walked sequentially, reshuffled when exhausted."""
+
+    def __init__(self, num_elements: int) -> None:
+        self.num_elements = num_elements
+        self.order = torch.randperm(num_elements)
+        self.cursor = 0
+
+    def get(self, num_samples: int = 1) -> torch.Tensor:
+        out = []
+        for _ in range(num_samples):
+            if self.cursor >= self.num_elements:
+                self.order = torch.randperm(self.num_elements)
+                self.cursor = 0
+            out.append(self.order[self.cursor])
+            self.cursor += 1
+        return torch.stack(out)
+
+
+class DatasetSampler:
+    """One random view per call, then random pixels of that view (DatasetSamplers.py:10-41)."""
+
+    def __init__(self, dataset, random: bool = True, img_sampler_cls=RandomImageSampler) -> None:
+        self.mode = dataset.mode
+        self.id_sampler = RandomSequentialSampler(len(dataset))
+        self.img_samplers = [img_sampler_cls(v.camera.width * v.camera.height) for v in dataset]
+
+    def get(self, dataset, ray_batch_size: int | None = None) -> dict:
+        if dataset.mode != self.mode:
+            raise Framework.SamplerError(f'sampler initialised for mode "{self.mode}", dataset is in mode "{dataset.mode}"')
+        sample_id = int(self.id_sampler.get(1).item())
+        view = dataset[sample_id]
+        ray_ids = ray_batch = None
+        if ray_batch_size is not None:
+            ray_ids = self.img_samplers[sample_id].get(ray_batch_size).to(Framework.config.GLOBAL.DEFAULT_DEVICE)
+            collection = dataset.ray_collection[self.mode]
+            ray_batch = (collection[sample_id] if collection is not None else view.get_rays())[ray_ids]
+        return {'sample_id': sample_id, 'view': view, 'image_sampler': self.img_samplers[sample_id], 'ray_ids': ray_ids,
+                'ray_batch': ray_batch}
+
+
+class RayPoolSampler:
+    """Random rays from the pool of all training rays (DatasetSamplers.py:44-66)."""
+
+    def __init__(self, dataset, img_sampler_cls=RandomImageSampler) -> None:
+        self.mode = dataset.mode
+        self.image_sampler = img_sampler_cls(dataset.get_total_ray_count())
+
+    def get(self, dataset, ray_batch_size: int) -> dict:
+        if dataset.mode != self.mode:
+            raise Framework.SamplerError(f'sampler initialised for mode "{self.mode}", dataset is in mode "{dataset.mode}"')
+        rays_all = dataset.get_all_rays()
+        ray_ids = self.image_sampler.get(ray_batch_size).to(rays_all.device)
+        return {'sample_id': None, 'view': None, 'image_sampler': self.image_sampler, 'ray_ids': ray_ids,
+                'ray_batch': rays_all[ray_ids].to(device=Framework.config.GLOBAL.DEFAULT_DEVICE)}

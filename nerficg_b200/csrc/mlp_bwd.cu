@@ -1,0 +1,332 @@
+// mlp_bwd.cu -- K4a: the data-gradient ("dgrad") chain of the NeRF MLP as one fused, persistent,
+// warp-specialised tcgen05 kernel (mirror image of mlp_fwd.cu).
+//
+// Per 128-sample tile, starting from dL/d(r,g,b,sigma_raw) (K6 output, loss-scaled):
+//   prologue : sigmoid' and W_c1^T on CUDA cores -> dL/dg (masked by g > 0)            [128 wide]
+//   stage 0  : dL/df   = dG  * W_c0[:, :256]
+//   stage 1  : dL/dh7  = (dF * W_f + dsigma_raw (x) w_sigma) . [h7 > 0]
+//   stage 2+j: dL/dh_{6-j} = (dY_{7-j} * W_{7-j}[:, :256]) . [h_{6-j} > 0],  j = 0..6
+// Every dY image (fp16, 128B-swizzled panels) is bulk-stored to the gradient stash for the
+// layer-major weight-gradient kernel (mlp_wgrad.cu).  Gradients are fp16 with a static loss scale:
+// mixed bf16 x fp16 UMMA operands are illegal on sm_100a and the stashed activations are fp16.
+#include "common.cuh"
+#include "mlp_layout.cuh"
+#include "tc.cuh"
+#include "../../include/nerf_b200.h"
+
+namespace nerf {
+using namespace tc;
+
+namespace bwd {
+constexpr int kThreads = 384;
+constexpr int kRingStages = 3;
+constexpr uint32_t kRingStageBytes = kPanelBytes256;
+constexpr uint32_t kSlotBytes = kActBytes;
+constexpr uint32_t kOffRing = 2 * kSlotBytes;
+constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
+constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+}  // namespace bwd
+
+struct BwdParams {
+  const float4* d_rgbsigma;
+  const float4* rgbsigma;
+  const uint8_t* stash;
+  uint8_t* gstash;
+  const uint8_t* packed;
+  const float* params;
+  int64_t n_evals;
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
+  using namespace bwd;
+  using L = ParamLayout;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + kOffBars;
+  const uint32_t bar_w_full = bars;
+  const uint32_t bar_w_empty = bars + 8 * kRingStages;
+  const uint32_t bar_a_ready = bars + 16 * kRingStages;
+  const uint32_t bar_acc_ready = bar_a_ready + 16;
+  const uint32_t bar_load = bar_acc_ready + 16;  // [2] G image landed in shared memory
+  const uint32_t tmem_slot = bar_load + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingStages; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_a_ready + 8 * s, 128);
+      mbar_init(bar_acc_ready + 8 * s, 1);
+      mbar_init(bar_load + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int pairs_total = (p.n_tiles + 1) / 2;
+  const int n_iters = (pairs_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+  const uint8_t* wimg = p.packed + kBwdImageOffset;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < n_iters; ++it)
+        for (int st = 0; st < kBwdStages; ++st)
+          for (int slot = 0; slot < 2; ++slot) {
+            if (tile_of(it, slot) >= p.n_tiles) continue;
+            const int first = bwd_first_panel(st), np = bwd_panels(st);
+            for (int pp = 0; pp < np; ++pp) {
+              mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(bar_w_full + 8 * stage, kPanelBytes256);
+              bulk_g2s(smem_base + kOffRing + stage * kRingStageBytes, wimg + (uint32_t)(first + pp) * kPanelBytes256,
+                       kPanelBytes256, bar_w_full + 8 * stage);
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_phase[2] = {0, 0};
+      constexpr uint32_t idesc = make_idesc(128, 256, kF16, kF16, 0, 0);
+      for (int it = 0; it < n_iters; ++it)
+        for (int st = 0; st < kBwdStages; ++st)
+          for (int slot = 0; slot < 2; ++slot) {
+            if (tile_of(it, slot) >= p.n_tiles) continue;
+            const uint32_t act = smem_base + slot * kSlotBytes;
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]);
+            a_phase[slot] ^= 1;
+            tc_fence_after();
+            const int np = bwd_panels(st);
+            uint32_t accumulate = 0;
+            for (int pp = 0; pp < np; ++pp) {
+              mbar_wait(bar_w_full + 8 * stage, phase);
+              tc_fence_after();
+              const uint32_t a_panel = act + pp * kPanelBytes128;
+              const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
+              for (int ks = 0; ks < 4; ++ks) {
+                umma(d_tmem, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(bar_w_empty + 8 * stage);
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            umma_commit(bar_acc_ready + 8 * slot);
+          }
+    }
+  } else if (warp >= 4) {
+    const int slot = (warp - 4) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int tg = threadIdx.x - 128 - slot * 128;
+    const uint32_t act = smem_base + slot * kSlotBytes;
+    const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t bar_id = 1 + slot;
+    uint32_t acc_phase = 0, load_phase = 0;
+    const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile = tile_of(it, slot);
+      if (tile >= p.n_tiles) break;
+      const int64_t e = (int64_t)tile * kTile + row;
+      const bool valid = e < p.n_evals;
+
+      auto gstash_store = [&](int region, uint32_t src, uint32_t bytes) {
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (tg == 0) {
+          bulk_s2g(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes);
+          bulk_commit();
+        }
+      };
+      auto gstash_drain = [&]() {
+        if (tg == 0) bulk_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+      };
+      const uint8_t* mask_base = p.stash + stash_region_offset(kStashMask, n_tiles64) +
+                                 (uint64_t)tile * stash_region_tile_bytes(kStashMask) + row * 32;
+
+      // ---------------- prologue ----------------
+      gstash_drain();  // previous tile's D0 store still reads act
+      if (tg == 0) {   // G image (2 panels) -> act panels 2,3
+        mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
+        bulk_g2s(act + 2 * kPanelBytes128,
+                 p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
+                 2 * kPanelBytes128, bar_load + 8 * slot);
+      }
+      float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dsr = 0.f;
+      if (valid) {
+        const float4 dd = __ldg(p.d_rgbsigma + e);
+        const float4 o = __ldg(p.rgbsigma + e);
+        dp0 = dd.x * o.x * (1.f - o.x);
+        dp1 = dd.y * o.y * (1.f - o.y);
+        dp2 = dd.z * o.z * (1.f - o.z);
+        dsr = dd.w;
+      }
+      {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
+        uint8_t* hd = p.gstash + grad_region_offset(kGradHead, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(kGradHead);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (ch == 0) {
+            v.x = pack_half2(dp0, dp1);
+            v.y = pack_half2(dp2, dsr);
+          }
+          *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, ch)) = v;
+        }
+      }
+      mbar_wait(bar_load + 8 * slot, load_phase);
+      load_phase ^= 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float dg[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
+          dg[4 * q + 0] = dp0 * w0.x + dp1 * w1.x + dp2 * w2.x;
+          dg[4 * q + 1] = dp0 * w0.y + dp1 * w1.y + dp2 * w2.y;
+          dg[4 * q + 2] = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
+          dg[4 * q + 3] = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
+        }
+        const uint32_t gpanel = act + (2 + (c0 >> 6)) * kPanelBytes128;
+        const uint32_t dpanel = act + (c0 >> 6) * kPanelBytes128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = panel_chunk_offset(row, ((c0 & 63) >> 3) + q);
+          uint32_t g0, g1, g2, g3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(gpanel + off));
+          const uint32_t gw[4] = {g0, g1, g2, g3};
+          uint32_t outw[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
+            const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
+            outw[t] = pack_half2(lo ? dg[8 * q + 2 * t] : 0.f, hi ? dg[8 * q + 2 * t + 1] : 0.f);
+          }
+          st_shared_v4(dpanel + off, outw[0], outw[1], outw[2], outw[3]);
+        }
+      }
+      gstash_store(kGradC0, act, 2 * kPanelBytes128);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_a_ready + 8 * slot);
+
+      // ---------------- chain stages ----------------
+#pragma unroll 1
+      for (int st = 0; st < kBwdStages; ++st) {
+        mbar_wait(bar_acc_ready + 8 * slot, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
+        const int mask_layer = 8 - st;  // valid for st >= 1
+        gstash_drain();                 // previous image store still reads act
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + c0, v);
+          uint32_t m = 0xffffffffu;
+          if (st >= 1) m = __ldg(reinterpret_cast<const uint32_t*>(mask_base + mask_layer * (128 * 32)) + (c0 >> 5));
+          float ws[32];
+          if (st == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWS + c0) + q);
+              ws[4 * q] = w4.x, ws[4 * q + 1] = w4.y, ws[4 * q + 2] = w4.z, ws[4 * q + 3] = w4.w;
+            }
+          }
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = __uint_as_float(v[j]);
+            if (st == 1) t = fmaf(dsr, ws[j], t);
+            x[j] = ((m >> j) & 1u) ? t : 0.f;
+          }
+          const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(x[8 * q], x[8 * q + 1]),
+                         pack_half2(x[8 * q + 2], x[8 * q + 3]), pack_half2(x[8 * q + 4], x[8 * q + 5]),
+                         pack_half2(x[8 * q + 6], x[8 * q + 7]));
+          }
+        }
+        gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
+        if (st < kBwdStages - 1) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_a_ready + 8 * slot);
+        } else {
+          tc_fence_before();  // accumulator drained; released by the next tile's prologue arrive
+        }
+      }
+    }
+    if (tg == 0) bulk_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_wgrad(float* grads, const uint8_t* stash, const uint8_t* gstash, int n_tiles, float inv_scale, cudaStream_t stream);
+
+}  // namespace nerf
+
+extern "C" size_t nerf_mlp_backward_workspace_bytes(int64_t n_samples) {
+  const uint64_t n_tiles = (uint64_t)((n_samples + nerf::kTile - 1) / nerf::kTile);
+  return (size_t)(nerf::grad_tile_bytes_total() * n_tiles);
+}
+
+extern "C" int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                                 const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
+                                 void* stream) {
+  using namespace nerf;
+  if (n_rays <= 0) return 0;
+  NERF_CHECK_ARG(grads && d_rgbsigma && rgbsigma && stash && workspace && packed && params, "mlp_backward: null pointer");
+  NERF_CHECK_ARG(grad_scale > 0.f, "mlp_backward: grad_scale must be positive");
+  const int64_t n_evals = (int64_t)n_rays * n_samples;
+  NERF_CHECK_ARG(n_evals < (int64_t(1) << 31) - kTile, "mlp_backward: n_rays*n_samples must be < 2^31 per call");
+  NERF_CHECK_ARG(((reinterpret_cast<uintptr_t>(stash) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(packed)) & 127) == 0,
+                 "mlp_backward: stash, workspace and packed must be 128-byte aligned");
+  BwdParams p;
+  p.d_rgbsigma = reinterpret_cast<const float4*>(d_rgbsigma);
+  p.rgbsigma = reinterpret_cast<const float4*>(rgbsigma);
+  p.stash = static_cast<const uint8_t*>(stash);
+  p.gstash = static_cast<uint8_t*>(workspace);
+  p.packed = static_cast<const uint8_t*>(packed);
+  p.params = params;
+  p.n_evals = n_evals;
+  p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
+    NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
+    attr_set = true;
+  }
+  const int pairs = (p.n_tiles + 1) / 2;
+  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  mlp_dgrad_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+  NERF_CHECK_LAUNCH("mlp_dgrad_kernel");
+  return launch_wgrad(grads, p.stash, p.gstash, p.n_tiles, 1.f / grad_scale, static_cast<cudaStream_t>(stream));
+}

@@ -101,7 +101,7 @@ def frequency_encoding(x: torch.Tensor, n_freq: int, append_input: bool = True) 
 
 def mlp_forward(sd: dict, prefix: str, positions: torch.Tensor, directions: torch.Tensor,
                 noise: Optional[torch.Tensor] = None, n_freq_pos: int = 10, n_freq_dir: int = 4,
-                n_layers: int = 8, skips=(5,), return_intermediates: bool = False):
+                n_layers: int = 8, skips=(5,), return_intermediates: bool = False, operand_dtype=None):
     """Density (N,1) and colour (N,3) of one NeRF block.
 
     Restates ``NeRFBlock.forward`` (src/Methods/NeRF/Model.py:59-83) functionally
@@ -110,13 +110,23 @@ def mlp_forward(sd: dict, prefix: str, positions: torch.Tensor, directions: torc
     features before the layers listed in ``skips``; density = ReLU(linear + noise);
     colour = sigmoid(W2 ReLU(W1 [feature, enc(dir)])).  ``noise`` is the already
     scaled additive density noise (std * randn) or None.
+
+    ``operand_dtype`` (e.g. torch.float16) is NOT part of the reference: it rounds the operands of
+    the ten tensor-core GEMMs (hidden layers, feature layer, first colour layer) the way the CUDA
+    path does (fp32 accumulate, fp32 heads), so tests can separate operand rounding from real bugs.
     """
+    def lin(x, w, b):
+        if operand_dtype is not None:  # straight-through rounding: gradients stay fp32
+            x = x + (x.to(operand_dtype).float() - x).detach()
+            w = w + (w.to(operand_dtype).float() - w).detach()
+        return torch.nn.functional.linear(x, w, b)
+
     ex = frequency_encoding(positions, n_freq_pos)
     h = ex
     inter = {}
     for l in range(n_layers):
         w, b = sd[f'{prefix}initial_layers.{l}.0.weight'], sd[f'{prefix}initial_layers.{l}.0.bias']
-        h = torch.relu(torch.nn.functional.linear(h, w, b))
+        h = torch.relu(lin(h, w, b))
         inter[f'h{l}'] = h
         if (l + 1) in skips:
             h = torch.cat((h, ex), dim=-1)
@@ -125,9 +135,8 @@ def mlp_forward(sd: dict, prefix: str, positions: torch.Tensor, directions: torc
         raw = raw + noise
     sigma = torch.relu(raw)
     ed = frequency_encoding(directions, n_freq_dir)
-    feat = torch.nn.functional.linear(h, sd[f'{prefix}feature_layer.weight'], sd[f'{prefix}feature_layer.bias'])
-    g = torch.relu(torch.nn.functional.linear(torch.cat((feat, ed), dim=-1),
-                                              sd[f'{prefix}color_layers.0.weight'], sd[f'{prefix}color_layers.0.bias']))
+    feat = lin(h, sd[f'{prefix}feature_layer.weight'], sd[f'{prefix}feature_layer.bias'])
+    g = torch.relu(lin(torch.cat((feat, ed), dim=-1), sd[f'{prefix}color_layers.0.weight'], sd[f'{prefix}color_layers.0.bias']))
     rgb = torch.sigmoid(torch.nn.functional.linear(g, sd[f'{prefix}color_layers.2.weight'], sd[f'{prefix}color_layers.2.bias']))
     if return_intermediates:
         inter.update(feat=feat, g=g, raw=raw)
