@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark contract of the B200-native NeRF hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one full NeRF training iteration (BASELINE.json configs[1]: 800x800 synthetic Lego-shaped views,
+4096-ray batch per GPU, 64 coarse + 128 fine samples, fp16 tensor-core MLP with fp32 accumulate, Adam step
+included).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for what every field means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_RAYS, N_COARSE, N_FINE = 4096, 64, 128
+WIDTH = HEIGHT = 800
+N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 64 B = 0.66 GB)
+METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
+# algorithmic work: MACs per MLP evaluation
+FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
+KERNELS_PER_STEP = 14       # pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {'workload': f'vanilla NeRF (nerf_lego model) training step, {WIDTH}x{HEIGHT} synthetic Lego-shaped views, '
+                        f'{N_RAYS}-ray batch per GPU, {N_COARSE} coarse + {N_FINE} fine samples/ray',
+            'rays_per_step_per_gpu': N_RAYS, 'n_coarse': N_COARSE, 'n_fine': N_FINE,
+            'global_rays_per_step': N_RAYS * n_gpus,
+            'parallelism': 'single GPU' if n_gpus == 1 else f'data parallel x{n_gpus}: per-rank ray batches, NCCL all-reduce of the flat MLP gradient',
+            'l2': 'working set per step (9.5 GB of activation/gradient stash) exceeds the 126 MB L2; no explicit flush needed'}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int) -> None:
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def __exit__(self, *_):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': int(float(self.samples[0][1])), 'reasons': reasons,
+                'power_w_max': max(float(s[2]) for s in self.samples), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; /root/reference is absent on the GPU box)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_factory(n_rays: int):
+    from oracle import nerf_oracle as O
+    sd = {k: v.clone().requires_grad_('frequency' not in k) for k, v in O.init_state_dict(0).items()}
+    opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=5e-4)
+    g = torch.Generator().manual_seed(0)
+    o = torch.randn(n_rays, 3, generator=g) * 0.1 + torch.tensor([0.0, -4.0, 0.5])
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g) * 0.2 + torch.tensor([0.0, 1.0, -0.1]), dim=-1) * 1.05
+    v = torch.nn.functional.normalize(d, dim=-1)
+    rgb, alpha, bg = torch.rand(n_rays, 3, generator=g), torch.ones(n_rays, 1), torch.ones(3)
+
+    def step():
+        out = O.render_rays(sd, o, d, v, 2.0, 6.0, bg, N_COARSE, N_FINE, torch.rand(n_rays, N_COARSE), torch.rand(n_rays, N_FINE))
+        loss = O.nerf_loss(out, rgb, alpha, bg)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu(n_rays: int, steps: int, warmup: int) -> float:
+    step = cpu_train_step_factory(n_rays)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return n_rays * steps / (time.perf_counter() - t0)
+
+
+def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's own CPU implementation of the path = its algorithm restated in
+    oracle/nerf_oracle.py (pinned to the reference by tests/golden), all host threads, bounded sample per step."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    threads = torch.get_num_threads()
+    probe = 128
+    step = cpu_train_step_factory(probe)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_ray = (time.perf_counter() - t0) / probe
+    budget = 150.0 / max(args.steps + args.warmup, 1)           # seconds per step so the whole run stays within minutes
+    n_rays = int(min(N_RAYS, max(64, budget / per_ray)))
+    value = time_cpu(n_rays, args.steps, args.warmup)
+    sample = f'{n_rays}-ray training steps ({N_COARSE}+{N_FINE} samples, fp32 PyTorch autograd + Adam) of the {N_RAYS}-ray workload'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * n_rays / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
+        'data': 'synthetic', 'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks() -> tuple[dict, str]:
+    path = ROOT / 'MEASURED_PEAKS.json'
+    if path.exists():
+        return json.loads(path.read_text()), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+def instrumented_kernel_times(trainer, step_obj, reps: int = 3) -> dict:
+    """Per-kernel device time of one training iteration: the same call sequence as the captured step, run eagerly
+    with a CUDA event pair around every C-ABI launch on the launching (current) stream."""
+    from nerficg_b200 import ops
+    s = step_obj
+    n, dev = s.n, s.dev
+    flats = [b.flat_params for b in s.blocks]
+    times: dict[str, list[float]] = {}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        times.setdefault(name, []).append((a, b))
+        return out
+
+    for _ in range(reps):
+        for flat, packed in zip(flats, s.packed):
+            timed('pack', lambda: ops.mlp_pack(flat, packed, True))
+        u_c = torch.rand((n, s.nc), device=dev)
+        z_c = timed('K1_stratified', lambda: ops.sample_stratified(n, s.nc, s.near, s.far, u_c, dev))
+        rs_c = timed('K3_mlp_fwd_coarse', lambda: ops.mlp_forward(s.packed[0], flats[0], s.origin, s.direction, s.view_direction, z_c, None, s.stash[0]))
+        rgb_c, _, _, w_c = timed('K5_composite_fwd_coarse', lambda: ops.composite_forward(z_c, rs_c, s.direction, s.bg, True))
+        u_f = torch.rand(n, s.nf, device=dev)
+        z = timed('K2_importance', lambda: ops.sample_importance(z_c, w_c, s.nf, u_f))
+        rs_f = timed('K3_mlp_fwd_fine', lambda: ops.mlp_forward(s.packed[1], flats[1], s.origin, s.direction, s.view_direction, z, None, s.stash[1]))
+        rgb, _, _, _ = timed('K5_composite_fwd_fine', lambda: ops.composite_forward(z, rs_f, s.direction, s.bg))
+        g = (rgb - s.rgb_gt) * (2.0 / rgb.numel())
+        grads = [torch.zeros_like(f) for f in flats]
+        d_rs = timed('K6_composite_bwd_fine', lambda: ops.composite_backward(z, rs_f, s.direction, s.bg, g, None, None, True, s.scale))
+        timed('K4a_mlp_dgrad_fine', lambda: ops.mlp_backward_dgrad(d_rs, rs_f, s.stash[1], s.ws, s.packed[1], flats[1], n, z.shape[1]))
+        timed('K4b_mlp_wgrad_fine', lambda: ops.mlp_backward_wgrad(grads[1], s.stash[1], s.ws, n, z.shape[1], s.scale))
+        g_c = (rgb_c - s.rgb_gt) * (2.0 / rgb_c.numel())
+        d_rs_c = timed('K6_composite_bwd_coarse', lambda: ops.composite_backward(z_c, rs_c, s.direction, s.bg, g_c, None, None, True, s.scale))
+        timed('K4a_mlp_dgrad_coarse', lambda: ops.mlp_backward_dgrad(d_rs_c, rs_c, s.stash[0], s.ws, s.packed[0], flats[0], n, s.nc))
+        timed('K4b_mlp_wgrad_coarse', lambda: ops.mlp_backward_wgrad(grads[0], s.stash[0], s.ws, n, s.nc, s.scale))
+    torch.cuda.synchronize()
+    return {k: sum(a.elapsed_time(b) for a, b in v[1:]) / max(len(v) - 1, 1) * (2 if k == 'pack' else 1) for k, v in times.items()}
+
+
+def run_gpu_arm(args) -> None:
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    from nerficg_b200 import Framework
+    Framework.setup(None, {'RENDERER.N_SAMPLES': N_COARSE + N_FINE, 'RENDERER.COARSE_RATIO': N_COARSE / (N_COARSE + N_FINE) + 1e-7,
+                           'TRAINING.BATCH_SIZE': N_RAYS, 'TRAINING.NUM_ITERATIONS': 500000, 'GLOBAL.LOG_LEVEL': 0}, device_index=local_rank)
+    dev = Framework.config.GLOBAL.DEFAULT_DEVICE
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    from nerficg_b200.Datasets import RayBatch
+    from nerficg_b200.Datasets.Synthetic import SyntheticLegoDataset
+    from nerficg_b200.Implementations import Methods
+
+    torch.manual_seed(0)                         # identical initial weights on every rank
+    trainer = Methods.get_training_instance('NeRF')
+    model, renderer = trainer.model, trainer.renderer
+    assert (renderer.n_samples_coarse_nerf, renderer.n_samples_nerf) == (N_COARSE, N_FINE)
+    torch.manual_seed(1000 + rank)               # per-rank ray batches and sampling noise
+    dataset = SyntheticLegoDataset(WIDTH, HEIGHT, N_TRAIN_VIEWS, 2, seed=rank, device=dev)
+    dataset.precompute_rays(['train'])
+    pool = dataset.ray_collection['train'].all_rays
+    camera = dataset.default_camera
+    n_pool = len(pool)
+
+    def device_batch() -> RayBatch:
+        return pool[torch.randint(0, n_pool, (N_RAYS,), device=dev)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (>= 3; the first two fused steps run eagerly, the third captures the CUDA graph) ----
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        trainer.fused_step(device_batch(), camera)
+    sync_all()
+
+    # ---- timed region A: inputs resident in HBM, device-timed, max over ranks ----
+    batches = [device_batch() for _ in range(min(args.steps, 64))]
+    sync_all()
+    with ClockSampler(local_rank) as clocks:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(args.steps):
+            trainer.fused_step(batches[i % len(batches)], camera)
+        end.record()
+        sync_all()
+        elapsed_ms = start.elapsed_time(end)
+        # ---- timed region B (end to end): pinned host buffers -> H2D copy every step, loss read back every step ----
+        host = []
+        for b in batches[:8]:
+            host.append({k: getattr(b, k).cpu().pin_memory() for k in ('origin', 'direction', 'view_direction', 'rgb', 'alpha')})
+        h2d = sum(t.numel() * 4 for t in host[0].values())
+        sync_all()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        losses = []
+        for i in range(args.steps):
+            hb = host[i % len(host)]
+            rb = RayBatch(**{k: v.to(dev, non_blocking=True) for k, v in hb.items()}, _skip_post_init=True)
+            losses.append(trainer.fused_step(rb, camera).item())    # D2H read of the step's loss
+        e_end.record()
+        sync_all()
+        e2e_ms = e_start.elapsed_time(e_end)
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = t.tolist()
+    value = N_RAYS * world * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = N_RAYS * world * args.steps / (e2e_ms * 1e-3)
+
+    # ---- rendering throughput (second half of the metric): one 800x800 test view per rank, ray-sharded, no comms ----
+    view = dataset.test()[rank % len(dataset.test())]
+    dataset.train()
+    with torch.no_grad():
+        rays = view.get_rays()
+        renderer.RAY_BATCH_SIZE = 65536
+        renderer.render_rays(rays[:65536], view.camera)
+        sync_all()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        renderer.render_rays(rays, view.camera)
+        r1.record()
+        sync_all()
+        render_ms = r0.elapsed_time(r1)
+    if world > 1:
+        t = torch.tensor([render_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        render_ms = t.item()
+    render_mrays = len(rays) * world / (render_ms * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (rank 0): live CUDA-event timing of every launch of one iteration ----
+    peaks, peak_source = measured_peaks()
+    kt = instrumented_kernel_times(trainer, trainer._fused[N_RAYS])
+    evals = {'coarse': N_RAYS * N_COARSE, 'fine': N_RAYS * (N_COARSE + N_FINE)}
+    n_tiles = {k: (v + 127) // 128 for k, v in evals.items()}
+    table = {}
+    for name, ms in kt.items():
+        which = 'coarse' if name.endswith('coarse') else 'fine'
+        row = {'ms': round(ms, 4)}
+        if name.startswith('K3'):
+            row.update(bound='tensor', achieved=FLOP_FWD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
+        elif name.startswith('K4a'):
+            row.update(bound='tensor', achieved=FLOP_DGRAD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
+        elif name.startswith('K4b'):   # operands re-read from the stashes: 1424 KB per 128-sample tile
+            row.update(bound='hbm', achieved=1424 * 1024 * n_tiles[which] / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
+                       tensor_tflops=FLOP_WGRAD * evals[which] / ms / 1e9)
+        elif name.startswith('K5'):
+            s = N_COARSE if which == 'coarse' else N_COARSE + N_FINE
+            row.update(bound='hbm', achieved=N_RAYS * ((24 if which == 'coarse' else 20) * s + 32) / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s')
+        elif name.startswith('K6'):
+            s = N_COARSE if which == 'coarse' else N_COARSE + N_FINE
+            row.update(bound='hbm', achieved=N_RAYS * (36 * s + 48) / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s')
+        if 'achieved' in row:
+            row['frac'] = row['achieved'] / row['peak']
+        table[name] = row
+    total_kernel_ms = sum(r['ms'] for r in table.values())
+    for r in table.values():
+        r['share'] = round(r['ms'] / total_kernel_ms, 4)
+    dom_name = max((k for k in table if 'achieved' in table[k]), key=lambda k: table[k]['ms'])
+    dom = table[dom_name]
+    roofline = {'kernel': dom_name, 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': dom['unit'],
+                'frac': dom['frac'], 'traffic': None, 'peak_source': peak_source + ('; sustained figure: the kernel is timed inside a long step' if dom['bound'] == 'tensor' else ''),
+                'ms_per_launch': dom['ms'], 'share_of_step': dom['share'],
+                'mlp_tensor_tflops_whole_step': (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * (evals['coarse'] + evals['fine']) / (elapsed_ms / args.steps) / 1e9}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+    threads = torch.get_num_threads()
+    cpu_rays = 1024
+    cpu_value = time_cpu(cpu_rays, steps=3, warmup=1)
+    cpu_baseline = {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                    'sample': f'3 training steps of {cpu_rays} rays ({N_COARSE}+{N_FINE} samples) of the same workload, fp32 PyTorch oracle, {os.cpu_count()} logical CPUs'}
+
+    print(json.dumps({
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'fp16 operands, fp32 accumulate (fp32 sampling/compositing/optimizer)', 'data': 'synthetic', 'config': workload_config(world),
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
+                'last_loss': losses[-1]},
+        'gpu_launches': KERNELS_PER_STEP * args.steps, 'clocks': clocks.summary(),
+        'roofline': roofline, 'kernels': table, 'cpu_baseline': cpu_baseline,
+        'render': {'metric': 'nerf_render_mrays_per_s', 'value': render_mrays, 'unit': 'Mrays/s', 'rays_per_gpu': len(rays),
+                   'ms': render_ms, 'tensor_tflops': FLOP_FWD * (N_COARSE + N_COARSE + N_FINE) * len(rays) * world / render_ms / 1e9},
+    }), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

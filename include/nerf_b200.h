@@ -104,6 +104,14 @@ int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsig
                       const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
                       void* stream);
 
+/* The two phases of nerf_mlp_backward, separately launchable (profiling, overlap with NCCL):
+ * dgrad walks the chain backwards per tile and fills `workspace` with the per-layer output gradients;
+ * wgrad reduces activations x gradients over all samples into `grads` (layer-major, HBM-bound). */
+int nerf_mlp_backward_dgrad(const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                            const void* packed, const float* params, int n_rays, int n_samples, void* stream);
+int nerf_mlp_backward_wgrad(float* grads, const void* stash, const void* workspace, int n_rays, int n_samples,
+                            float grad_scale, void* stream);
+
 /* ---- self test of the tcgen05 building blocks (used by tests/ only) --------------------
  * D[128][n] = A[128][k] * B[n][k]^T with operand images built on device; mode selects the
  * descriptor flavour (0: K-major fp16, 1: MN-major operands as in wgrad, 2: K-major bf16). */

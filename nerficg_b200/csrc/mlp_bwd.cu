@@ -298,12 +298,12 @@ extern "C" size_t nerf_mlp_backward_workspace_bytes(int64_t n_samples) {
   return (size_t)(nerf::grad_tile_bytes_total() * n_tiles);
 }
 
-extern "C" int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
-                                 const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
-                                 void* stream) {
+static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                        const void* packed, const float* params, int n_rays, int n_samples, float grad_scale, void* stream,
+                        int phases) {
   using namespace nerf;
   if (n_rays <= 0) return 0;
-  NERF_CHECK_ARG(grads && d_rgbsigma && rgbsigma && stash && workspace && packed && params, "mlp_backward: null pointer");
+  NERF_CHECK_ARG(stash && workspace, "mlp_backward: null pointer");
   NERF_CHECK_ARG(grad_scale > 0.f, "mlp_backward: grad_scale must be positive");
   const int64_t n_evals = (int64_t)n_rays * n_samples;
   NERF_CHECK_ARG(n_evals < (int64_t(1) << 31) - kTile, "mlp_backward: n_rays*n_samples must be < 2^31 per call");
@@ -318,15 +318,39 @@ extern "C" int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const fl
   p.params = params;
   p.n_evals = n_evals;
   p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
-    NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
-    attr_set = true;
+  if (phases & 1) {
+    NERF_CHECK_ARG(d_rgbsigma && rgbsigma && packed && params, "mlp_backward: null pointer");
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
+      NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
+      attr_set = true;
+    }
+    const int pairs = (p.n_tiles + 1) / 2;
+    const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+    mlp_dgrad_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    NERF_CHECK_LAUNCH("mlp_dgrad_kernel");
   }
-  const int pairs = (p.n_tiles + 1) / 2;
-  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
-  mlp_dgrad_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-  NERF_CHECK_LAUNCH("mlp_dgrad_kernel");
-  return launch_wgrad(grads, p.stash, p.gstash, p.n_tiles, 1.f / grad_scale, static_cast<cudaStream_t>(stream));
+  if (phases & 2) {
+    NERF_CHECK_ARG(grads != nullptr, "mlp_backward: null gradient buffer");
+    return launch_wgrad(grads, p.stash, p.gstash, p.n_tiles, 1.f / grad_scale, static_cast<cudaStream_t>(stream));
+  }
+  return 0;
+}
+
+extern "C" int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                                 const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
+                                 void* stream) {
+  return run_backward(grads, d_rgbsigma, rgbsigma, stash, workspace, packed, params, n_rays, n_samples, grad_scale, stream, 3);
+}
+
+extern "C" int nerf_mlp_backward_dgrad(const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                                       const void* packed, const float* params, int n_rays, int n_samples, void* stream) {
+  return run_backward(nullptr, d_rgbsigma, rgbsigma, stash, workspace, packed, params, n_rays, n_samples, 1.f, stream, 1);
+}
+
+extern "C" int nerf_mlp_backward_wgrad(float* grads, const void* stash, const void* workspace, int n_rays, int n_samples,
+                                       float grad_scale, void* stream) {
+  return run_backward(grads, nullptr, nullptr, stash, const_cast<void*>(workspace), nullptr, nullptr, n_rays, n_samples,
+                      grad_scale, stream, 2);
 }

@@ -124,6 +124,20 @@ def mlp_backward(grads_flat: torch.Tensor, d_rgbsigma: torch.Tensor, rgbsigma: t
           'nerf_mlp_backward')
 
 
+def mlp_backward_dgrad(d_rgbsigma, rgbsigma, stash, workspace, packed, params_flat, n_rays: int, n_samples: int) -> None:
+    """K4a only: fills ``workspace`` with the per-layer output gradients."""
+    require_device(d_rgbsigma)
+    check(load().nerf_mlp_backward_dgrad(ptr(d_rgbsigma), ptr(rgbsigma), ptr(stash), ptr(workspace), ptr(packed),
+                                         ptr(params_flat), n_rays, n_samples, stream_ptr()), 'nerf_mlp_backward_dgrad')
+
+
+def mlp_backward_wgrad(grads_flat, stash, workspace, n_rays: int, n_samples: int, grad_scale: float = 1.0) -> None:
+    """K4b only: accumulates weight/bias gradients from the two stashes."""
+    require_device(grads_flat)
+    check(load().nerf_mlp_backward_wgrad(ptr(grads_flat), ptr(stash), ptr(workspace), n_rays, n_samples, float(grad_scale),
+                                         stream_ptr()), 'nerf_mlp_backward_wgrad')
+
+
 def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     """D = A @ B^T on one 128-row tile through tcgen05 (tests only)."""
     a, b = _f32c(a), _f32c(b)
