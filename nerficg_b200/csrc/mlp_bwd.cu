@@ -19,8 +19,8 @@ using namespace tc;
 
 namespace bwd {
 constexpr int kThreads = 384;
-constexpr int kRingStages = 3;
-constexpr uint32_t kRingStageBytes = kPanelBytes256;
+constexpr int kRingStages = 6;                           // 16 KB stages (64 inputs x 128 outputs), see mlp_fwd.cu
+constexpr uint32_t kRingStageBytes = kPanelBytes128;
 constexpr uint32_t kSlotBytes = kActBytes;
 constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
@@ -83,19 +83,23 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t keep = l2_evict_last();
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (tile_of(it, slot) >= p.n_tiles) continue;
             const int first = bwd_first_panel(st), np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
-              mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(bar_w_full + 8 * stage, kPanelBytes256);
-              bulk_g2s(smem_base + kOffRing + stage * kRingStageBytes, wimg + (uint32_t)(first + pp) * kPanelBytes256,
-                       kPanelBytes256, bar_w_full + 8 * stage);
-              if (++stage == kRingStages) {
-                stage = 0;
-                phase ^= 1;
+              for (int nh = 0; nh < 2; ++nh) {
+                mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
+                bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
+                              wimg + (uint32_t)(first + pp) * kPanelBytes256 + nh * kRingStageBytes, kRingStageBytes,
+                              bar_w_full + 8 * stage, keep);
+                if (++stage == kRingStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
           }
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      constexpr uint32_t idesc = make_idesc(128, 256, kF16, kF16, 0, 0);
+      constexpr uint32_t idesc = make_idesc(128, 128, kF16, kF16, 0, 0);
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
@@ -115,20 +119,19 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = bwd_panels(st);
-            uint32_t accumulate = 0;
             for (int pp = 0; pp < np; ++pp) {
-              mbar_wait(bar_w_full + 8 * stage, phase);
-              tc_fence_after();
               const uint32_t a_panel = act + pp * kPanelBytes128;
-              const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
-              for (int ks = 0; ks < 4; ++ks) {
-                umma(d_tmem, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(bar_w_empty + 8 * stage);
-              if (++stage == kRingStages) {
-                stage = 0;
-                phase ^= 1;
+              for (int nh = 0; nh < 2; ++nh) {
+                mbar_wait(bar_w_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
+                for (int ks = 0; ks < 4; ++ks)
+                  umma(d_tmem + nh * 128, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc, (pp | ks) != 0);
+                umma_commit(bar_w_empty + 8 * stage);
+                if (++stage == kRingStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
             umma_commit(bar_acc_ready + 8 * slot);
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (tg == 0) {
-          bulk_s2g(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes);
+          bulk_s2g_hint(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes,
+                        l2_evict_first());
           bulk_commit();
         }
       };
@@ -170,9 +174,9 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
       gstash_drain();  // previous tile's D0 store still reads act
       if (tg == 0) {   // G image (2 panels) -> act panels 2,3
         mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
-        bulk_g2s(act + 2 * kPanelBytes128,
-                 p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
-                 2 * kPanelBytes128, bar_load + 8 * slot);
+        bulk_g2s_hint(act + 2 * kPanelBytes128,
+                      p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
+                      2 * kPanelBytes128, bar_load + 8 * slot, l2_evict_first());
       }
       float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dsr = 0.f;
       if (valid) {

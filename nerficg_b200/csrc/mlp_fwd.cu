@@ -26,8 +26,10 @@ using namespace tc;
 
 namespace fwd {
 constexpr int kThreads = 384;
-constexpr int kRingStages = 2;
-constexpr uint32_t kRingStageBytes = kPanelBytes256;
+// weight ring: 16 KB stages = one K panel (64 inputs) x 128 output neurons.  Smaller stages keep more bytes in
+// flight for the same shared memory (the chain is weight-latency-bound: ~97 KB in flight would saturate the MMA pipe)
+constexpr int kRingStages = 4;
+constexpr uint32_t kRingStageBytes = kPanelBytes128;
 // shared memory map (offsets from the 1024-aligned base)
 constexpr uint32_t kSlotBytes = kActBytes + kPanelBytes128;  // act (4 panels) + enc (1 panel)
 constexpr uint32_t kOffRing = 2 * kSlotBytes;
@@ -127,20 +129,24 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     // =============================== weight producer ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t keep = l2_evict_last();
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
             if (tile_of(it, slot) >= p.n_tiles) continue;
             const int first = fwd_first_panel(st), np = fwd_panels(st);
+            const int halves = st == 9 ? 1 : 2;  // 128-row chunks per panel
             for (int pp = 0; pp < np; ++pp) {
-              mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
-              const uint32_t bytes = fwd_panel_bytes(first + pp);
-              mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
-              bulk_g2s(smem_base + kOffRing + stage * kRingStageBytes, p.packed + fwd_panel_offset(first + pp), bytes,
-                       bar_w_full + 8 * stage);
-              if (++stage == kRingStages) {
-                stage = 0;
-                phase ^= 1;
+              for (int nh = 0; nh < halves; ++nh) {
+                mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
+                bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
+                              p.packed + fwd_panel_offset(first + pp) + nh * kRingStageBytes, kRingStageBytes,
+                              bar_w_full + 8 * stage, keep);
+                if (++stage == kRingStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
           }
@@ -152,7 +158,6 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      constexpr uint32_t idesc256 = make_idesc(128, 256, kF16, kF16, 0, 0);
       constexpr uint32_t idesc128 = make_idesc(128, 128, kF16, kF16, 0, 0);
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
@@ -165,22 +170,22 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = fwd_panels(st);
-            uint32_t accumulate = 0;
+            const int halves = st == 9 ? 1 : 2;
             for (int pp = 0; pp < np; ++pp) {
               // A operand: stage 0 reads the encoding panel; panel 4 of stages 5 / 9 is the encoding / direction panel
               const uint32_t a_panel = (st == 0 || pp == 4) ? enc : act + pp * kPanelBytes128;
               const int ksteps = (st == 9 && pp == 4) ? 2 : 4;
-              mbar_wait(bar_w_full + 8 * stage, phase);
-              tc_fence_after();
-              const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                umma(d_tmem, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), st == 9 ? idesc128 : idesc256, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(bar_w_empty + 8 * stage);
-              if (++stage == kRingStages) {
-                stage = 0;
-                phase ^= 1;
+              for (int nh = 0; nh < halves; ++nh) {
+                mbar_wait(bar_w_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
+                for (int ks = 0; ks < ksteps; ++ks)
+                  umma(d_tmem + nh * 128, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc128, (pp | ks) != 0);
+                umma_commit(bar_w_empty + 8 * stage);
+                if (++stage == kRingStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
             umma_commit(bar_acc_ready + 8 * slot);
@@ -214,7 +219,8 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
           if (tg == 0) {
-            bulk_s2g(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes);
+            bulk_s2g_hint(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes,
+                          l2_evict_first());
             bulk_commit();
           }
         }

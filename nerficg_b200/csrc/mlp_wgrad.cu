@@ -19,10 +19,10 @@ using namespace tc;
 
 namespace wg {
 constexpr int kThreads = 256;  // warp 0 producer, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 reduce + flush
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;
 constexpr uint32_t kHalfPanel = 8192;       // 64 rows x 128 B
-constexpr uint32_t kStageBytes = 8 * kHalfPanel;
-constexpr uint32_t kOffBars = kStages * kStageBytes;
+constexpr uint32_t kRingBytes = 24 * kHalfPanel;  // 192 KB, carved into as many stages as the job's operands allow
+constexpr uint32_t kOffBars = kRingBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 constexpr int kNumJobs = 13;
 
@@ -82,10 +82,14 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + kOffBars;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_done = bars + 16 * kStages, tmem_slot = bar_done + 8;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages, bar_done = bars + 16 * kMaxStages, tmem_slot = bar_done + 8;
+  // jobs with small operands (head, encoding) get more, smaller stages: every job keeps ~190 KB of loads in flight,
+  // otherwise those CTAs are latency-bound and finish long after the 64 KB-per-stage jobs (measured: SMs 58 % active)
+  const uint32_t kStageBytes = (uint32_t)(c_jobs[job_idx].a.panels + c_jobs[job_idx].b[0].panels + c_jobs[job_idx].b[1].panels) * kHalfPanel;
+  const int kStages = (int)(kRingBytes / kStageBytes) < kMaxStages ? (int)(kRingBytes / kStageBytes) : kMaxStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 2);  // MMA commit + reducer group
     }
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t stream_policy = l2_evict_first();
       for (int step = 0; step < n_steps; ++step) {
         const int tile = tile_lo + (step >> 1), half = step & 1;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
         for (int s = 0; s < 3; ++s) {
           const uint8_t* src = region_ptr(*segs[s], tile) + half * kHalfPanel;
           for (int pp = 0; pp < segs[s]->panels; ++pp) {
-            bulk_g2s(dst, src + (uint64_t)pp * region_panel_bytes(*segs[s]), kHalfPanel, bar_full + 8 * stage);
+            bulk_g2s_hint(dst, src + (uint64_t)pp * region_panel_bytes(*segs[s]), kHalfPanel, bar_full + 8 * stage, stream_policy);
             dst += kHalfPanel;
           }
         }

@@ -57,8 +57,8 @@ def test_forward_vs_oracle(ops, net, n_rays, s):
     assert torch.equal(out_t.cpu().reshape(-1, 4), out)
 
 
-def _rel_l2(a, b):
-    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+def _rel_l2(a, b, floor=0.0):
+    return ((a - b).norm() / (b.norm() + floor + 1e-30)).item()
 
 
 @pytest.mark.parametrize('n_rays,s,scale', [(64, 64, 1024.0), (300, 192, 4096.0), (5, 77, 2048.0), (2048, 64, 1024.0)])
@@ -101,8 +101,11 @@ def test_backward_vs_oracle(ops, net, n_rays, s, scale):
     ops.mlp_backward(grads, up_dev, out, stash, ws, packed['nerf.'], flat['nerf.'], n_rays, s, scale)
     torch.cuda.synchronize()
     got = P.views(grads.cpu())
-    e16 = {k: round(_rel_l2(v, ref['fp16'][k]), 4) for k, v in got.items()}
-    e32 = {k: round(_rel_l2(v, ref['fp32'][k]), 4) for k, v in got.items()}
+    # the 1- and 3-element head biases are plain sums of the upstream gradients: with few samples they cancel to
+    # nearly zero, so their error is measured against the size of the summands rather than of the (tiny) sum
+    floor = {k: (0.05 * up.norm().item() if v.numel() <= 3 else 0.0) for k, v in got.items()}
+    e16 = {k: round(_rel_l2(v, ref['fp16'][k], floor[k]), 4) for k, v in got.items()}
+    e32 = {k: round(_rel_l2(v, ref['fp32'][k], floor[k]), 4) for k, v in got.items()}
     import json, os
     os.makedirs('gpurun_out', exist_ok=True)
     with open('gpurun_out/grad_parity.jsonl', 'a') as f:
