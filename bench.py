@@ -231,6 +231,13 @@ def run_gpu_arm(args) -> None:
     for _ in range(warmup):
         trainer.fused_step(device_batch(), camera)
     sync_all()
+    if args.profile_steps > 0:   # ncu --profile-from-start off: only these graph replays are captured (never a bench value)
+        torch.cuda.profiler.start()
+        for _ in range(args.profile_steps):
+            trainer.fused_step(device_batch(), camera)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     # ---- timed region A: inputs resident in HBM, device-timed, max over ranks ----
     batches = [device_batch() for _ in range(min(args.steps, 64))]
@@ -354,6 +361,7 @@ def main() -> None:
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--profile-steps', type=int, default=0, help='run N steps between cudaProfilerStart/Stop and exit (for ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -112,6 +112,11 @@ int nerf_mlp_backward_dgrad(const float* d_rgbsigma, const float* rgbsigma, cons
 int nerf_mlp_backward_wgrad(float* grads, const void* stash, const void* workspace, int n_rays, int n_samples,
                             float grad_scale, void* stream);
 
+/* ---- stall accounting (development aid, tools/kernel_timing.py) ---------------------------
+ * Registers a device buffer of 32 uint64 counters (or NULL to switch it off, the default): the MLP kernels
+ * then add the cycles selected threads spent waiting on each barrier (slot meaning: DESIGN.md "Stall accounting"). */
+int nerf_debug_set_timing(void* device_buffer);
+
 /* ---- self test of the tcgen05 building blocks (used by tests/ only) --------------------
  * D[128][n] = A[128][k] * B[n][k]^T with operand images built on device; mode selects the
  * descriptor flavour (0: K-major fp16, 1: MN-major operands as in wgrad, 2: K-major bf16). */

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import torch
 
-from ... import Framework, ops, params
+from ... import Framework, dist, ops, params
 from ...Logging import Logger
 from ...Optim.lr_utils import LRDecayPolicy
 from ...Optim.Samplers import DatasetSampler, RandomImageSampler, RayPoolSampler
@@ -151,7 +151,7 @@ class _FusedStep:
         # persistent flat gradient buffers; parameter .grad fields are views into them
         self.grads = [torch.zeros_like(b.flat_params) for b in self.blocks]
         self.scale = default_grad_scale(n_rays)
-        self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.world = dist.world_size()
         self.graph = None
         self.use_graph = use_graph
         self.calls = 0
@@ -208,10 +208,7 @@ class _FusedStep:
                 g_alpha_c = (dac * (2.0 * la / dac.numel())).reshape(-1)
             d_rs_c = ops.composite_backward(z_c, rs_c, self.direction, self.bg, g_rgb_c, None, g_alpha_c, True, self.scale)
             ops.mlp_backward(self.grads[0], d_rs_c, rs_c, self.stash[0], self.ws, self.packed[0], flats[0], n, self.nc, self.scale)
-        if self.world > 1:
-            for g in self.grads:
-                torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM)
-                g.mul_(1.0 / self.world)
+        dist.allreduce_mean_(self.grads)
         self.loss_out.copy_(loss)
         t.optimizer.step()
 

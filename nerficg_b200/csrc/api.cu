@@ -13,7 +13,14 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+static uint64_t* g_timing = nullptr;
+uint64_t* timing_buffer() { return g_timing; }
 }  // namespace nerf
+
+extern "C" int nerf_debug_set_timing(void* device_buffer) {
+  nerf::g_timing = static_cast<uint64_t*>(device_buffer);
+  return 0;
+}
 
 extern "C" int nerf_abi_version(void) { return NERF_ABI_VERSION; }
 extern "C" const char* nerf_last_error(void) { return nerf::g_error; }

@@ -57,6 +57,17 @@ struct ParamLayout {
   __host__ __device__ static constexpr int hidden_in(int l) { return l == 0 ? 63 : (l == 5 ? 319 : 256); }
 };
 
+// Optional in-kernel stall accounting (tools/kernel_timing.py): when a timing buffer is registered through
+// nerf_debug_set_timing(), selected threads accumulate the cycles they spend in each wait and add them to
+// the buffer at exit.  A null buffer (the default) costs one predictable branch per wait.
+uint64_t* timing_buffer();  // api.cu (host-side registry)
+#define NERF_TIMED(enabled, acc, stmt)              \
+  do {                                              \
+    const long long t0__ = (enabled) ? clock64() : 0; \
+    stmt;                                           \
+    if (enabled) acc += clock64() - t0__;           \
+  } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

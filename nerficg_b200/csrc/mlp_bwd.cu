@@ -37,6 +37,7 @@ struct BwdParams {
   const float* params;
   int64_t n_evals;
   int n_tiles;
+  unsigned long long* prof;  // optional stall counters, slots 10..19 (same meaning as the forward's 0..9)
 };
 
 __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
+      const bool prof = p.prof != nullptr;
+      long long t_wait = 0;
+      const long long t_begin = prof ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
             const int first = bwd_first_panel(st), np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               for (int nh = 0; nh < 2; ++nh) {
-                mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+                NERF_TIMED(prof, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
                               wimg + (uint32_t)(first + pp) * kPanelBytes256 + nh * kRingStageBytes, kRingStageBytes,
@@ -103,11 +107,18 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
               }
             }
           }
+      if (prof) {
+        atomicAdd(p.prof + 13, (unsigned long long)t_wait);
+        atomicAdd(p.prof + 14, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
+      const bool prof = p.prof != nullptr;
+      long long t_a = 0, t_w = 0;
+      const long long t_begin = prof ? clock64() : 0;
       constexpr uint32_t idesc = make_idesc(128, 128, kF16, kF16, 0, 0);
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
@@ -115,14 +126,14 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
             if (tile_of(it, slot) >= p.n_tiles) continue;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]);
+            NERF_TIMED(prof, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               const uint32_t a_panel = act + pp * kPanelBytes128;
               for (int nh = 0; nh < 2; ++nh) {
-                mbar_wait(bar_w_full + 8 * stage, phase);
+                NERF_TIMED(prof, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
                 tc_fence_after();
                 const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
                 for (int ks = 0; ks < 4; ++ks)
@@ -136,6 +147,12 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
             }
             umma_commit(bar_acc_ready + 8 * slot);
           }
+      if (prof) {
+        atomicAdd(p.prof + 10, (unsigned long long)t_a);
+        atomicAdd(p.prof + 11, (unsigned long long)t_w);
+        atomicAdd(p.prof + 12, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(p.prof + 19, 1ull);
+      }
     }
   } else if (warp >= 4) {
     const int slot = (warp - 4) >> 2;
@@ -147,6 +164,9 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     const uint32_t bar_id = 1 + slot;
     uint32_t acc_phase = 0, load_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+    const bool prof = p.prof != nullptr && tg == 0 && slot == 0;
+    long long t_accw = 0, t_drain = 0, t_pro = 0;
+    const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
       const int tile = tile_of(it, slot);
@@ -164,13 +184,16 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         }
       };
       auto gstash_drain = [&]() {
+        const long long t0 = prof ? clock64() : 0;
         if (tg == 0) bulk_wait_read<0>();
         named_bar_sync(bar_id, 128);
+        if (prof) t_drain += clock64() - t0;
       };
       const uint8_t* mask_base = p.stash + stash_region_offset(kStashMask, n_tiles64) +
                                  (uint64_t)tile * stash_region_tile_bytes(kStashMask) + row * 32;
 
       // ---------------- prologue ----------------
+      const long long t_tile = prof ? clock64() : 0;
       gstash_drain();  // previous tile's D0 store still reads act
       if (tg == 0) {   // G image (2 panels) -> act panels 2,3
         mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
@@ -236,11 +259,12 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_a_ready + 8 * slot);
+      if (prof) t_pro += clock64() - t_tile;
 
       // ---------------- chain stages ----------------
 #pragma unroll 1
       for (int st = 0; st < kBwdStages; ++st) {
-        mbar_wait(bar_acc_ready + 8 * slot, acc_phase);
+        NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
@@ -287,6 +311,12 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
       }
     }
     if (tg == 0) bulk_wait_all<0>();
+    if (prof) {
+      atomicAdd(p.prof + 15, (unsigned long long)t_accw);
+      atomicAdd(p.prof + 16, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(p.prof + 17, (unsigned long long)t_drain);
+      atomicAdd(p.prof + 18, (unsigned long long)t_pro);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -322,6 +352,7 @@ static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbs
   p.params = params;
   p.n_evals = n_evals;
   p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
+  p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
   if (phases & 1) {
     NERF_CHECK_ARG(d_rgbsigma && rgbsigma && packed && params, "mlp_backward: null pointer");
     static bool attr_set = false;

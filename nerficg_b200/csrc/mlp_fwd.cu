@@ -52,6 +52,7 @@ struct FwdParams {
   int n_samples;    // S
   int64_t n_evals;  // n_rays * S
   int n_tiles;
+  unsigned long long* prof;  // optional stall counters (common.cuh NERF_TIMED), slots 0..9
 };
 
 // ---- per-row input encoding ----------------------------------------------------------------
@@ -130,6 +131,9 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
+      const bool prof = p.prof != nullptr;
+      long long t_wait = 0;
+      const long long t_begin = prof ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
             const int halves = st == 9 ? 1 : 2;  // 128-row chunks per panel
             for (int pp = 0; pp < np; ++pp) {
               for (int nh = 0; nh < halves; ++nh) {
-                mbar_wait(bar_w_empty + 8 * stage, phase ^ 1);
+                NERF_TIMED(prof, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
                               p.packed + fwd_panel_offset(first + pp) + nh * kRingStageBytes, kRingStageBytes,
@@ -152,12 +156,19 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
           }
         }
       }
+      if (prof) {
+        atomicAdd(p.prof + 3, (unsigned long long)t_wait);
+        atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
+      const bool prof = p.prof != nullptr;
+      long long t_a = 0, t_w = 0;
+      const long long t_begin = prof ? clock64() : 0;
       constexpr uint32_t idesc128 = make_idesc(128, 128, kF16, kF16, 0, 0);
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t enc = act + kActBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]);
+            NERF_TIMED(prof, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = fwd_panels(st);
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
               const uint32_t a_panel = (st == 0 || pp == 4) ? enc : act + pp * kPanelBytes128;
               const int ksteps = (st == 9 && pp == 4) ? 2 : 4;
               for (int nh = 0; nh < halves; ++nh) {
-                mbar_wait(bar_w_full + 8 * stage, phase);
+                NERF_TIMED(prof, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
                 tc_fence_after();
                 const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
                 for (int ks = 0; ks < ksteps; ++ks)
@@ -192,6 +203,12 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
           }
         }
       }
+      if (prof) {
+        atomicAdd(p.prof + 0, (unsigned long long)t_a);
+        atomicAdd(p.prof + 1, (unsigned long long)t_w);
+        atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(p.prof + 9, 1ull);
+      }
     }
   } else if (warp >= 4) {
     // =============================== epilogue warpgroups ===============================
@@ -205,10 +222,14 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     const uint32_t bar_id = 1 + slot;  // named barrier of this warpgroup
     uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+    const bool prof = p.prof != nullptr && tg == 0 && slot == 0;
+    long long t_accw = 0, t_drain = 0, t_pro = 0;
+    const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
       const int tile = tile_of(it, slot);
       if (tile >= p.n_tiles) break;
+      const long long t_tile = prof ? clock64() : 0;
       const int64_t e = (int64_t)tile * kTile + row;  // sample index
       const bool valid = e < p.n_evals;
       const int ray = valid ? (int)(e / p.n_samples) : 0;
@@ -228,8 +249,10 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       // before overwriting a buffer that may still be read by an in-flight bulk store
       auto stash_drain = [&]() {
         if (kTrain) {
+          const long long t0 = prof ? clock64() : 0;
           if (tg == 0) bulk_wait_read<0>();
           named_bar_sync(bar_id, 128);
+          if (prof) t_drain += clock64() - t0;
         }
       };
 
@@ -261,12 +284,13 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_a_ready + 8 * slot);
+      if (prof) t_pro += clock64() - t_tile;
 
       float sigma = 0.f;
       // ---------------- chain stages ----------------
 #pragma unroll 1
       for (int st = 0; st < kFwdStages; ++st) {
-        mbar_wait(bar_acc_ready + 8 * slot, acc_phase);
+        NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         if (st < 9) {
@@ -392,6 +416,12 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       }
     }
     if (kTrain && tg == 0) bulk_wait_all<0>();
+    if (prof) {
+      atomicAdd(p.prof + 5, (unsigned long long)t_accw);
+      atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(p.prof + 7, (unsigned long long)t_drain);
+      atomicAdd(p.prof + 8, (unsigned long long)t_pro);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -431,6 +461,7 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
   p.n_samples = n_samples;
   p.n_evals = n_evals;
   p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
+  p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
   const int pairs = (p.n_tiles + 1) / 2;
   const int grid = pairs < kNumSMs ? pairs : kNumSMs;
   static bool attr_set = false;

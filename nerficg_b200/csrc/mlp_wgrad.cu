@@ -116,24 +116,38 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
     return s.buf == 0 ? gstash + grad_region_offset(s.region, nt) + (uint64_t)tile * grad_region_tile_bytes(s.region)
                       : stash + stash_region_offset(s.region, nt) + (uint64_t)tile * stash_region_tile_bytes(s.region);
   };
-  auto region_panel_bytes = [&](const Seg& s) -> uint32_t { return kPanelBytes128; };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint64_t stream_policy = l2_evict_first();
+      // per-segment source cursors, computed once: the region tables are runtime loops and one thread issues
+      // every copy of this CTA (measured: with the lookups inside the loop the producer was 75 % issue-busy and
+      // the kernel ran at 4.3 TB/s; DESIGN.md "K4b")
+      const Seg* segs[3] = {&job.a, &job.b[0], &job.b[1]};
+      const uint8_t* cur[3];
+      uint32_t tile_stride[3];
+      int panels[3];
+      for (int s = 0; s < 3; ++s) {
+        panels[s] = segs[s]->panels;
+        cur[s] = region_ptr(*segs[s], tile_lo);
+        tile_stride[s] = segs[s]->buf == 0 ? grad_region_tile_bytes(segs[s]->region) : stash_region_tile_bytes(segs[s]->region);
+      }
+      const uint32_t stage_bytes = (uint32_t)(na + nb0 + nb1) * kHalfPanel;
       for (int step = 0; step < n_steps; ++step) {
-        const int tile = tile_lo + (step >> 1), half = step & 1;
+        const uint32_t half_off = (step & 1) * kHalfPanel;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(na + nb0 + nb1) * kHalfPanel);
+        mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
         uint32_t dst = smem_base + stage * kStageBytes;
-        const Seg* segs[3] = {&job.a, &job.b[0], &job.b[1]};
+#pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const uint8_t* src = region_ptr(*segs[s], tile) + half * kHalfPanel;
-          for (int pp = 0; pp < segs[s]->panels; ++pp) {
-            bulk_g2s_hint(dst, src + (uint64_t)pp * region_panel_bytes(*segs[s]), kHalfPanel, bar_full + 8 * stage, stream_policy);
+          const uint8_t* src = cur[s] + half_off;
+          for (int pp = 0; pp < panels[s]; ++pp) {
+            bulk_g2s_hint(dst, src, kHalfPanel, bar_full + 8 * stage, stream_policy);
             dst += kHalfPanel;
+            src += kPanelBytes128;
           }
+          if (step & 1) cur[s] += tile_stride[s];
         }
         if (++stage == kStages) {
           stage = 0;

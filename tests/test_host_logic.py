@@ -1,0 +1,95 @@
+"""CPU: host-side mirror of the reference's plugin interface (config, registry, model layout, schedule)."""
+import math
+
+import pytest
+import torch
+
+from nerficg_b200 import Framework, dist, params
+
+
+@pytest.fixture()
+def cfg():
+    Framework.load_config(None, {'RENDERER.N_SAMPLES': 192, 'RENDERER.COARSE_RATIO': 1 / 3 + 1e-7, 'GLOBAL.LOG_LEVEL': 0})
+    yield Framework.config
+
+
+def test_config_overrides_and_errors(cfg):
+    assert cfg.RENDERER.N_SAMPLES == 192
+    Framework.load_config(None, {'TRAINING.BATCH_SIZE': '4096', 'GLOBAL.LOG_LEVEL': 0})
+    assert Framework.config.TRAINING.BATCH_SIZE == 4096          # strings are literal_eval'ed like KEY=VAL overrides
+    with pytest.raises(Framework.FrameworkError):
+        Framework.load_config(None, {'NOPE.X.Y': 1, 'GLOBAL.LOG_LEVEL': 0})
+
+
+def test_plugin_triple_and_registry(cfg):
+    from nerficg_b200.Implementations import Methods, install_into_reference
+    mod = Methods.import_method('NeRF')
+    assert {mod.MODEL.__name__, mod.RENDERER.__name__, mod.TRAINING_INSTANCE.__name__} == {'NeRF', 'NeRFRenderer', 'NeRFTrainer'}
+    with pytest.raises(Framework.MethodError):
+        Methods.import_method('InstantNGP')
+
+    class FakeReference:            # stands for the reference's Implementations module
+        class Methods:
+            modules = {}
+    install_into_reference(FakeReference)
+    assert FakeReference.Methods.modules['NeRF'] is mod
+
+
+def test_model_state_dict_matches_reference_layout(cfg):
+    from nerficg_b200.Methods.NeRF.Model import NeRF
+    model = NeRF('t').build()
+    sd = model.state_dict()
+    for prefix in ('coarse_nerf.', 'nerf.'):
+        for name, shape in params.TENSOR_SPECS:
+            assert tuple(sd[prefix + name].shape) == shape
+        assert tuple(sd[prefix + 'encoding_position.frequency_factors'].shape) == (1, 1, 10)
+        assert tuple(sd[prefix + 'encoding_direction.frequency_factors'].shape) == (1, 1, 4)
+    assert sum(p.numel() for p in model.parameters()) == 1191688
+    # parameters are views into one flat buffer per block, in C-layout order
+    block = model.nerf
+    flat = block.flat_params
+    off, size, _ = params.layout()
+    for p, o in zip(block.ordered_parameters(), off):
+        assert p.data_ptr() == flat.data_ptr() + 4 * o
+    w = block.initial_layers[5][0].weight
+    assert tuple(w.shape) == (256, 319)                          # skip concat (h, enc) before layer 5
+    # same init distribution as nn.Linear default: U(+-1/sqrt(fan_in))
+    assert w.abs().max().item() <= 1 / math.sqrt(319) + 1e-7
+
+
+def test_unsupported_architecture_is_rejected(cfg):
+    from nerficg_b200.Methods.NeRF.Model import NeRFBlock
+    with pytest.raises(Framework.ModelError):
+        NeRFBlock(8, 1, 128, 10, 4, True, [5], 'relu')
+    with pytest.raises(Framework.ModelError):
+        NeRFBlock(8, 1, 256, 10, 4, True, [5], 'softplus')
+
+
+def test_renderer_sample_split_and_model_check(cfg):
+    from nerficg_b200.Methods.NeRF.Model import NeRF
+    from nerficg_b200.Methods.NeRF.Renderer import NeRFRenderer, default_grad_scale
+    r = NeRFRenderer(NeRF('t').build())
+    assert (r.n_samples_coarse_nerf, r.n_samples_nerf) == (64, 128)   # round(N_SAMPLES * COARSE_RATIO), Renderer.py:113-114
+    assert r.RAY_BATCH_SIZE == 8192
+    with pytest.raises(Framework.RendererError):
+        NeRFRenderer(torch.nn.Linear(1, 1))
+    assert default_grad_scale(4096) == 65536.0
+
+
+def test_lr_schedule_is_log_linear():
+    from nerficg_b200.Optim.lr_utils import LRDecayPolicy
+    f = LRDecayPolicy(lr_init=5e-4, lr_final=5e-5, max_steps=1000)
+    assert f(0) == pytest.approx(5e-4) and f(1000) == pytest.approx(5e-5) and f(5000) == pytest.approx(5e-5)
+    assert f(500) == pytest.approx(math.sqrt(5e-4 * 5e-5))
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in ((200, 8), (200, 3), (5, 8), (0, 4), (640000, 7)):
+        seen = []
+        for r in range(w):
+            seen += list(dist.shard_range(n, r, w))
+        assert seen == list(range(n))
+        sizes = [len(dist.shard_range(n, r, w)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        dist.shard_range(10, 4, 4)
