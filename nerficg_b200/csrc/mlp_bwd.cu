@@ -26,6 +26,8 @@ constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+static_assert(kRingStages % 2 == 0, "ring stages are consumed in pairs");
+constexpr int kRegsEpilogue = 232, kRegsOther = 40;
 }  // namespace bwd
 
 struct BwdParams {
@@ -39,6 +41,40 @@ struct BwdParams {
   int n_tiles;
   unsigned long long* prof;  // optional stall counters, slots 10..19 (same meaning as the forward's 0..9)
 };
+
+__device__ __forceinline__ void load8(float4 (&dst)[8], const float* src) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+}
+
+// One 32-column chunk of a dgrad epilogue: t = acc (+ dsigma_raw * w_sigma), masked by the forward ReLU bits
+// (tc.cuh relu_mask_bit layout) -> fp16 pairs -> swizzled A-operand chunk of the next stage.
+template <bool kSig>
+__device__ __forceinline__ void dgrad_chunk(const uint32_t (&v)[32], uint32_t m, const float4 (&ws)[8], float dsr,
+                                            uint32_t panel_row_base, int chunk_in_panel, int row) {
+  uint32_t w[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float t0 = __uint_as_float(v[4 * q + 0]), t1 = __uint_as_float(v[4 * q + 1]);
+    float t2 = __uint_as_float(v[4 * q + 2]), t3 = __uint_as_float(v[4 * q + 3]);
+    if (kSig) {
+      t0 = fmaf(dsr, ws[q].x, t0);
+      t1 = fmaf(dsr, ws[q].y, t1);
+      t2 = fmaf(dsr, ws[q].z, t2);
+      t3 = fmaf(dsr, ws[q].w, t3);
+    }
+    t0 = (m & (1u << (2 * q))) ? t0 : 0.f;
+    t1 = (m & (1u << (16 + 2 * q))) ? t1 : 0.f;
+    t2 = (m & (1u << (2 * q + 1))) ? t2 : 0.f;
+    t3 = (m & (1u << (16 + 2 * q + 1))) ? t3 : 0.f;
+    w[2 * q] = pack_half2(t0, t1);
+    w[2 * q + 1] = pack_half2(t2, t3);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    st_shared_v4(panel_row_base + ((((uint32_t)(chunk_in_panel + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1],
+                 w[4 * q + 2], w[4 * q + 3]);
+}
 
 __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
   using namespace bwd;
@@ -81,80 +117,86 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
   auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
   const uint8_t* wimg = p.packed + kBwdImageOffset;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  const bool prof_on = p.prof != nullptr;
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsOther>();
+    if (warp == 0) {
+      // weight producer: K' panel pp of stage st -> ring stages (2j, 2j+1) = the two 128-column halves of W^T
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
-      const bool prof = p.prof != nullptr;
       long long t_wait = 0;
-      const long long t_begin = prof ? clock64() : 0;
+      const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (tile_of(it, slot) >= p.n_tiles) continue;
             const int first = bwd_first_panel(st), np = bwd_panels(st);
-            for (int pp = 0; pp < np; ++pp) {
-              for (int nh = 0; nh < 2; ++nh) {
-                NERF_TIMED(prof, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
+            for (int j = 0; j < 2 * np; ++j) {
+              NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
+              if (elect_one()) {
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
-                              wimg + (uint32_t)(first + pp) * kPanelBytes256 + nh * kRingStageBytes, kRingStageBytes,
+                              wimg + (uint32_t)(first + (j >> 1)) * kPanelBytes256 + (j & 1) * kRingStageBytes, kRingStageBytes,
                               bar_w_full + 8 * stage, keep);
-                if (++stage == kRingStages) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+              }
+              __syncwarp();
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
               }
             }
           }
-      if (prof) {
+      if (prof_on && lane == 0) {
         atomicAdd(p.prof + 13, (unsigned long long)t_wait);
         atomicAdd(p.prof + 14, (unsigned long long)(clock64() - t_begin));
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1) {
+      // MMA issuer: warp-uniform loop, one elected lane issues N = 256 instructions (see mlp_fwd.cu)
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      const bool prof = p.prof != nullptr;
+      constexpr uint32_t idesc = make_idesc(128, 256, kF16, kF16, 0, 0);
       long long t_a = 0, t_w = 0;
-      const long long t_begin = prof ? clock64() : 0;
-      constexpr uint32_t idesc = make_idesc(128, 128, kF16, kF16, 0, 0);
+      const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (tile_of(it, slot) >= p.n_tiles) continue;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            NERF_TIMED(prof, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
+            NERF_TIMED(prof_on, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
-              const uint32_t a_panel = act + pp * kPanelBytes128;
-              for (int nh = 0; nh < 2; ++nh) {
-                NERF_TIMED(prof, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
-                tc_fence_after();
-                const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
-                for (int ks = 0; ks < 4; ++ks)
-                  umma(d_tmem + nh * 128, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc, (pp | ks) != 0);
+              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
+              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * (stage + 1), phase));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t da = make_smem_desc(act + pp * kPanelBytes128, 16u, kAtomBytes);
+                const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes, 16u, kAtomBytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
                 umma_commit(bar_w_empty + 8 * stage);
-                if (++stage == kRingStages) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+                umma_commit(bar_w_empty + 8 * (stage + 1));
+                if (pp == np - 1) umma_commit(bar_acc_ready + 8 * slot);
+              }
+              __syncwarp();
+              stage += 2;
+              if (stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
               }
             }
-            umma_commit(bar_acc_ready + 8 * slot);
           }
-      if (prof) {
+      if (prof_on && lane == 0) {
         atomicAdd(p.prof + 10, (unsigned long long)t_a);
         atomicAdd(p.prof + 11, (unsigned long long)t_w);
         atomicAdd(p.prof + 12, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 19, 1ull);
       }
     }
-  } else if (warp >= 4) {
+  } else {
+    setmaxnreg_inc<kRegsEpilogue>();
     const int slot = (warp - 4) >> 2;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
@@ -162,9 +204,10 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     const uint32_t act = smem_base + slot * kSlotBytes;
     const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;
+    const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
     uint32_t acc_phase = 0, load_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
-    const bool prof = p.prof != nullptr && tg == 0 && slot == 0;
+    const bool prof = prof_on && tg == 0 && slot == 0;
     long long t_accw = 0, t_drain = 0, t_pro = 0;
     const long long t_begin = prof ? clock64() : 0;
 
@@ -264,41 +307,34 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
       // ---------------- chain stages ----------------
 #pragma unroll 1
       for (int st = 0; st < kBwdStages; ++st) {
+        // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
+        const int mask_layer = 8 - st;  // valid for st >= 1
+        uint4 mk0 = make_uint4(~0u, ~0u, ~0u, ~0u), mk1 = mk0;
+        if (st >= 1) {  // ReLU masks of the whole row (8 words), in flight while the MMAs still run
+          const uint4* mp = reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32));
+          mk0 = __ldg(mp);
+          mk1 = __ldg(mp + 1);
+        }
+        const bool sig_stage = st == 1;  // dL/dh7 also receives dsigma_raw * w_sigma
+        float4 wa[8], wb[8];
+        if (sig_stage) load8(wa, p.params + L::kWS);
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
-        // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
-        const int mask_layer = 8 - st;  // valid for st >= 1
         gstash_drain();                 // previous image store still reads act
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        const uint32_t mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
           uint32_t v[32];
-          tmem_ld32(t_acc + c0, v);
-          uint32_t m = 0xffffffffu;
-          if (st >= 1) m = __ldg(reinterpret_cast<const uint32_t*>(mask_base + mask_layer * (128 * 32)) + (c0 >> 5));
-          float ws[32];
-          if (st == 1) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWS + c0) + q);
-              ws[4 * q] = w4.x, ws[4 * q + 1] = w4.y, ws[4 * q + 2] = w4.z, ws[4 * q + 3] = w4.w;
-            }
-          }
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(v[j]);
-            if (st == 1) t = fmaf(dsr, ws[j], t);
-            x[j] = ((m >> j) & 1u) ? t : 0.f;
-          }
-          const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(x[8 * q], x[8 * q + 1]),
-                         pack_half2(x[8 * q + 2], x[8 * q + 3]), pack_half2(x[8 * q + 4], x[8 * q + 5]),
-                         pack_half2(x[8 * q + 6], x[8 * q + 7]));
-          }
+          const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
+          tmem_ld32(t_acc + 32 * c, v);
+          if (sig_stage) load8(wb, p.params + L::kWS + 32 * (c + 1));
+          tmem_ld_wait32(v);
+          if (sig_stage) dgrad_chunk<true>(v, mk[c], wa, dsr, base, 0, row); else dgrad_chunk<false>(v, mk[c], wa, dsr, base, 0, row);
+          tmem_ld32(t_acc + 32 * (c + 1), v);
+          if (sig_stage && c + 2 < 8) load8(wa, p.params + L::kWS + 32 * (c + 2));
+          tmem_ld_wait32(v);
+          if (sig_stage) dgrad_chunk<true>(v, mk[c + 1], wb, dsr, base, 4, row); else dgrad_chunk<false>(v, mk[c + 1], wb, dsr, base, 4, row);
         }
         gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
         if (st < kBwdStages - 1) {

@@ -5,9 +5,10 @@
 // chain (mlp_layout.cuh) without touching HBM in between:
 //   warp 0      weight producer: streams fp16 weight panels (pre-swizzled UMMA images) from L2
 //               into a shared-memory ring with 1-D bulk copies (TMA engine) + mbarriers
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) from the
-//               slot's activation panels (A, shared memory) and the ring (B); accumulators live
-//               in TMEM (2 slots x 256 fp32 columns = all 512 columns)
+//   warp 1      MMA issuer: the warp runs the loop uniformly and ONE elected lane issues
+//               tcgen05.mma (M=128, N=256, K=16) from the slot's activation panels (A, shared
+//               memory) and a PAIR of ring stages (B: both 128-neuron halves of one K panel);
+//               accumulators live in TMEM (2 slots x 256 fp32 columns = all 512 columns)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue of slot 0 \  tcgen05.ld accumulator -> +bias, ReLU -> fp16 -> swizzled
 //   warps 8-11  epilogue of slot 1 /  A-operand panels of the next stage (in place); the two slots
@@ -16,6 +17,14 @@
 // the epilogues of stages 7 and 9, so the kernel emits packed (r,g,b,sigma) per sample.
 // Training additionally stashes every operand image the backward needs (bulk stores from shared
 // memory, region-major, see mlp_layout.cuh) and per-layer ReLU bit masks.
+//
+// Measured lessons baked into the structure (DESIGN.md "K3"):
+//   * the issuing warp must stay warp-uniform with elect.sync around the tcgen05 instructions: issued under
+//     `if (lane == 0)` every MMA was wrapped in a compiler-generated ELECT/BRA.U.ANY waterfall and cost ~190
+//     cycles of issue for 64 cycles of tensor work;
+//   * N = 256 per instruction halves the instruction count and the re-reads of the A operand;
+//   * the epilogue prefetches the next chunk's bias (and density weights) while it processes the
+//     current one and takes the registers the producer / MMA warps do not need (setmaxnreg).
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc.cuh"
@@ -26,8 +35,8 @@ using namespace tc;
 
 namespace fwd {
 constexpr int kThreads = 384;
-// weight ring: 16 KB stages = one K panel (64 inputs) x 128 output neurons.  Smaller stages keep more bytes in
-// flight for the same shared memory (the chain is weight-latency-bound: ~97 KB in flight would saturate the MMA pipe)
+// weight ring: 16 KB stages = one K panel (64 inputs) x 128 output neurons, consumed in PAIRS (stage 2j, 2j+1 are
+// adjacent in shared memory, so a pair is one 256-neuron B operand).
 constexpr int kRingStages = 4;
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 // shared memory map (offsets from the 1024-aligned base)
@@ -36,6 +45,8 @@ constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;  // + barriers + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+static_assert(kRingStages % 2 == 0, "ring stages are consumed in pairs");
+constexpr int kRegsEpilogue = 232, kRegsOther = 40;  // 256 * 232 + 128 * 40 = 64512 <= 65536
 }  // namespace fwd
 
 struct FwdParams {
@@ -86,6 +97,43 @@ __device__ __forceinline__ void write_row_panel(uint32_t panel_smem, int row, co
   }
 }
 
+__device__ __forceinline__ void load8(float4 (&dst)[8], const float* src) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+}
+
+// One 32-column chunk of a hidden-stage epilogue: x = acc + bias [ReLU] -> fp16 pairs -> swizzled A-operand chunk.
+// Returns the ReLU bit mask (tc.cuh relu_mask_bit layout); accumulates the density head when kDens.
+template <bool kDens>
+__device__ __forceinline__ uint32_t hidden_chunk(const uint32_t (&v)[32], const float4 (&b)[8], const float4 (&ws)[8], bool relu,
+                                                 uint32_t panel_row_base, int chunk_in_panel, int row, float& dens) {
+  uint32_t w[16];
+  uint32_t m = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float x0 = __uint_as_float(v[4 * q + 0]) + b[q].x;
+    float x1 = __uint_as_float(v[4 * q + 1]) + b[q].y;
+    float x2 = __uint_as_float(v[4 * q + 2]) + b[q].z;
+    float x3 = __uint_as_float(v[4 * q + 3]) + b[q].w;
+    if (relu) {
+      x0 = fmaxf(x0, 0.f);
+      x1 = fmaxf(x1, 0.f);
+      x2 = fmaxf(x2, 0.f);
+      x3 = fmaxf(x3, 0.f);
+    }
+    if (kDens) dens = fmaf(x0, ws[q].x, fmaf(x1, ws[q].y, fmaf(x2, ws[q].z, fmaf(x3, ws[q].w, dens))));
+    w[2 * q] = pack_half2(x0, x1);
+    w[2 * q + 1] = pack_half2(x2, x3);
+    m |= half2_gt0_mask(w[2 * q]) & (0x00010001u << (2 * q));
+    m |= half2_gt0_mask(w[2 * q + 1]) & (0x00010001u << (2 * q + 1));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    st_shared_v4(panel_row_base + ((((uint32_t)(chunk_in_panel + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1],
+                 w[4 * q + 2], w[4 * q + 3]);
+  return m;
+}
+
 template <bool kTrain>
 __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   using namespace fwd;
@@ -125,51 +173,58 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
   const int pairs_total = (p.n_tiles + 1) / 2;
   const int n_iters = (pairs_total + (int)gridDim.x - 1) / (int)gridDim.x;
   auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+  const bool prof_on = p.prof != nullptr;
 
-  if (warp == 0) {
-    // =============================== weight producer ===============================
-    if (lane == 0) {
+  if (warp < 4) {
+    setmaxnreg_dec<kRegsOther>();
+    if (warp == 0) {
+      // =============================== weight producer ===============================
+      // Every (stage, slot) consumes an even number of ring stages.  Stages 0..8: K panel pp -> ring stages
+      // (2j, 2j+1) = neuron halves 0 / 1.  Stage 9 (128 neurons): ring pair = K panels (2j, 2j+1); the 6th,
+      // non-existent panel is a zero-byte stage (plain arrive) so the pairing never shifts.
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
-      const bool prof = p.prof != nullptr;
       long long t_wait = 0;
-      const long long t_begin = prof ? clock64() : 0;
+      const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
             if (tile_of(it, slot) >= p.n_tiles) continue;
-            const int first = fwd_first_panel(st), np = fwd_panels(st);
-            const int halves = st == 9 ? 1 : 2;  // 128-row chunks per panel
-            for (int pp = 0; pp < np; ++pp) {
-              for (int nh = 0; nh < halves; ++nh) {
-                NERF_TIMED(prof, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
-                mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
-                bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
-                              p.packed + fwd_panel_offset(first + pp) + nh * kRingStageBytes, kRingStageBytes,
-                              bar_w_full + 8 * stage, keep);
-                if (++stage == kRingStages) {
-                  stage = 0;
-                  phase ^= 1;
+            const int first = fwd_first_panel(st);
+            const int n_stage_loads = st == 9 ? 6 : 2 * fwd_panels(st);
+            for (int j = 0; j < n_stage_loads; ++j) {
+              NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
+              if (elect_one()) {
+                if (st == 9 && j == 5) {
+                  mbar_arrive(bar_w_full + 8 * stage);
+                } else {
+                  const uint8_t* src = st == 9 ? p.packed + fwd_panel_offset(first + j)
+                                               : p.packed + fwd_panel_offset(first + (j >> 1)) + (j & 1) * kRingStageBytes;
+                  mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
+                  bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes, src, kRingStageBytes, bar_w_full + 8 * stage, keep);
                 }
+              }
+              __syncwarp();
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
               }
             }
           }
         }
       }
-      if (prof) {
+      if (prof_on && lane == 0) {
         atomicAdd(p.prof + 3, (unsigned long long)t_wait);
         atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
       }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    } else if (warp == 1) {
+      // =============================== MMA issuer ===============================
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      const bool prof = p.prof != nullptr;
-      long long t_a = 0, t_w = 0;
-      const long long t_begin = prof ? clock64() : 0;
+      constexpr uint32_t idesc256 = make_idesc(128, 256, kF16, kF16, 0, 0);
       constexpr uint32_t idesc128 = make_idesc(128, 128, kF16, kF16, 0, 0);
+      long long t_a = 0, t_w = 0;
+      const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
@@ -177,41 +232,60 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t enc = act + kActBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            NERF_TIMED(prof, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
+            NERF_TIMED(prof_on, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
-            const int np = fwd_panels(st);
-            const int halves = st == 9 ? 1 : 2;
-            for (int pp = 0; pp < np; ++pp) {
-              // A operand: stage 0 reads the encoding panel; panel 4 of stages 5 / 9 is the encoding / direction panel
-              const uint32_t a_panel = (st == 0 || pp == 4) ? enc : act + pp * kPanelBytes128;
-              const int ksteps = (st == 9 && pp == 4) ? 2 : 4;
-              for (int nh = 0; nh < halves; ++nh) {
-                NERF_TIMED(prof, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
-                tc_fence_after();
-                const uint32_t b_panel = smem_base + kOffRing + stage * kRingStageBytes;
-                for (int ks = 0; ks < ksteps; ++ks)
-                  umma(d_tmem + nh * 128, desc_kmajor(a_panel, ks), desc_kmajor(b_panel, ks), idesc128, (pp | ks) != 0);
-                umma_commit(bar_w_empty + 8 * stage);
-                if (++stage == kRingStages) {
-                  stage = 0;
-                  phase ^= 1;
+            const int n_steps = st == 9 ? 3 : fwd_panels(st);
+            for (int step = 0; step < n_steps; ++step) {
+              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
+              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * (stage + 1), phase));
+              tc_fence_after();
+              const uint32_t ring = smem_base + kOffRing + stage * kRingStageBytes;
+              if (elect_one()) {
+                if (st != 9) {
+                  // A: stage 0 reads the encoding panel; panel 4 of stage 5 is the retained encoding panel
+                  const uint64_t da = make_smem_desc((st == 0 || step == 4) ? enc : act + step * kPanelBytes128, 16u, kAtomBytes);
+                  const uint64_t db = make_smem_desc(ring, 16u, kAtomBytes);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc256, (step | ks) != 0);
+                } else {
+                  // two K panels of the 128-neuron colour layer per ring pair; panel 4 = direction encoding (32 wide)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const int pp = 2 * step + h;
+                    if (pp < 5) {
+                      const uint64_t da = make_smem_desc(pp == 4 ? enc : act + pp * kPanelBytes128, 16u, kAtomBytes);
+                      const uint64_t db = make_smem_desc(ring + h * kRingStageBytes, 16u, kAtomBytes);
+#pragma unroll
+                      for (int ks = 0; ks < 4; ++ks)
+                        if (pp < 4 || ks < 2) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc128, (pp | ks) != 0);
+                    }
+                  }
                 }
+                umma_commit(bar_w_empty + 8 * stage);
+                umma_commit(bar_w_empty + 8 * (stage + 1));
+                if (step == n_steps - 1) umma_commit(bar_acc_ready + 8 * slot);
+              }
+              __syncwarp();
+              stage += 2;
+              if (stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
               }
             }
-            umma_commit(bar_acc_ready + 8 * slot);
           }
         }
       }
-      if (prof) {
+      if (prof_on && lane == 0) {
         atomicAdd(p.prof + 0, (unsigned long long)t_a);
         atomicAdd(p.prof + 1, (unsigned long long)t_w);
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 9, 1ull);
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // =============================== epilogue warpgroups ===============================
+    setmaxnreg_inc<kRegsEpilogue>();
     const int slot = (warp - 4) >> 2;
     const int wq = warp & 3;                 // TMEM lane quarter of this warp
     const int row = wq * 32 + lane;          // row of the tile owned by this thread
@@ -220,9 +294,10 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     const uint32_t enc = act + kActBytes;
     const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;  // named barrier of this warpgroup
+    const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
     uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
-    const bool prof = p.prof != nullptr && tg == 0 && slot == 0;
+    const bool prof = prof_on && tg == 0 && slot == 0;
     long long t_accw = 0, t_drain = 0, t_pro = 0;
     const long long t_begin = prof ? clock64() : 0;
 
@@ -287,132 +362,131 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       if (prof) t_pro += clock64() - t_tile;
 
       float sigma = 0.f;
-      // ---------------- chain stages ----------------
+      // ---------------- chain stages 0..8: hidden layers (ReLU) and the feature layer (linear) ----------------
 #pragma unroll 1
-      for (int st = 0; st < kFwdStages; ++st) {
+      for (int st = 0; st < 9; ++st) {
+        const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF);
+        const bool relu = st < 8;
+        const bool dens_stage = st == 7;
+        float4 ba[8], bb[8], wa[8], wb[8];
+        load8(ba, bias);  // in flight while the MMAs of this stage still run
+        if (dens_stage) load8(wa, p.params + L::kWS);
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
-        if (st < 9) {
-          // hidden layers 0..7 (ReLU) and the feature layer (stage 8, linear)
-          const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF);
-          const bool relu = st < 8;
-          float dens = 0.f;
-          uint32_t* mask_dst = nullptr;
-          if (kTrain && relu)
-            mask_dst = reinterpret_cast<uint32_t*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
-                                                   (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
-          stash_drain();  // the act image of the previous stage may still be being stored
+        stash_drain();  // the act image of the previous stage may still be being stored
+        float dens = 0.f;
+        uint2* mask_dst = nullptr;
+        if (kTrain && relu)
+          mask_dst = reinterpret_cast<uint2*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
+                                              (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
 #pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
-            float bv[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
-              bv[4 * q] = b4.x, bv[4 * q + 1] = b4.y, bv[4 * q + 2] = b4.z, bv[4 * q + 3] = b4.w;
-            }
-            tmem_ld_wait();
-            float h[32];
-            uint32_t m = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]) + bv[j];
-              if (relu) {
-                m |= (x > 0.f ? 1u : 0u) << j;
-                x = fmaxf(x, 0.f);
-              }
-              h[j] = x;
-            }
-            if (kTrain && relu) mask_dst[c0 >> 5] = m;
-            if (st == 7) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWS + c0) + q);
-                dens = fmaf(h[4 * q], w4.x, dens);
-                dens = fmaf(h[4 * q + 1], w4.y, dens);
-                dens = fmaf(h[4 * q + 2], w4.z, dens);
-                dens = fmaf(h[4 * q + 3], w4.w, dens);
-              }
-            }
-            const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(h[8 * q], h[8 * q + 1]),
-                           pack_half2(h[8 * q + 2], h[8 * q + 3]), pack_half2(h[8 * q + 4], h[8 * q + 5]),
-                           pack_half2(h[8 * q + 6], h[8 * q + 7]));
-            }
+        for (int c = 0; c < 8; c += 2) {
+          uint32_t v[32];
+          uint32_t m0, m1;
+          // ---- chunk c: bias in ba (wa), prefetch chunk c+1 into bb (wb) ----
+          tmem_ld32(t_acc + 32 * c, v);
+          load8(bb, bias + 32 * (c + 1));
+          if (dens_stage) load8(wb, p.params + L::kWS + 32 * (c + 1));
+          tmem_ld_wait32(v);
+          {
+            const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
+            m0 = dens_stage ? hidden_chunk<true>(v, ba, wa, relu, base, 0, row, dens)
+                            : hidden_chunk<false>(v, ba, wa, relu, base, 0, row, dens);
           }
-          if (st == 7) {
-            float raw = dens + __ldg(p.params + L::kBS);
-            if (p.noise != nullptr && valid) raw += __ldg(p.noise + e);
-            sigma = fmaxf(raw, 0.f);
+          // ---- chunk c+1: bias in bb (wb), prefetch chunk c+2 into ba (wa) ----
+          tmem_ld32(t_acc + 32 * (c + 1), v);
+          if (c + 2 < 8) {
+            load8(ba, bias + 32 * (c + 2));
+            if (dens_stage) load8(wa, p.params + L::kWS + 32 * (c + 2));
           }
-          if (st == 8) {
-            // direction encoding -> enc panel (the x encoding was last read by stage 5)
-            float vals[64];
-            vals[0] = vdx;
-            vals[1] = vdy;
-            vals[2] = vdz;
-            encode_axis(vdx, 4, vals + 3);
-            encode_axis(vdy, 4, vals + 11);
-            encode_axis(vdz, 4, vals + 19);
-#pragma unroll
-            for (int j = 27; j < 64; ++j) vals[j] = 0.f;
-            write_row_panel(enc, row, vals);
-            stash_store(kStashDir, enc, kPanelBytes128);
+          tmem_ld_wait32(v);
+          {
+            const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
+            m1 = dens_stage ? hidden_chunk<true>(v, bb, wb, relu, base, 4, row, dens)
+                            : hidden_chunk<false>(v, bb, wb, relu, base, 4, row, dens);
           }
-          stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_a_ready + 8 * slot);
-        } else {
-          // stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores
-          float a0 = __ldg(p.params + L::kBC1 + 0), a1 = __ldg(p.params + L::kBC1 + 1), a2 = __ldg(p.params + L::kBC1 + 2);
-          stash_drain();  // the F image store reads act, which receives g below
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
-            tmem_ld_wait();
-            float g[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.params + L::kBC0 + c0) + q);
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
-              const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
-              g[4 * q + 0] = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
-              g[4 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
-              g[4 * q + 2] = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
-              g[4 * q + 3] = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
-              a0 = fmaf(g[4 * q + 0], w0.x, fmaf(g[4 * q + 1], w0.y, fmaf(g[4 * q + 2], w0.z, fmaf(g[4 * q + 3], w0.w, a0))));
-              a1 = fmaf(g[4 * q + 0], w1.x, fmaf(g[4 * q + 1], w1.y, fmaf(g[4 * q + 2], w1.z, fmaf(g[4 * q + 3], w1.w, a1))));
-              a2 = fmaf(g[4 * q + 0], w2.x, fmaf(g[4 * q + 1], w2.y, fmaf(g[4 * q + 2], w2.z, fmaf(g[4 * q + 3], w2.w, a2))));
-            }
-            if (kTrain) {
-              const uint32_t panel = act + (c0 >> 6) * kPanelBytes128;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                st_shared_v4(panel + panel_chunk_offset(row, ((c0 & 63) >> 3) + q), pack_half2(g[8 * q], g[8 * q + 1]),
-                             pack_half2(g[8 * q + 2], g[8 * q + 3]), pack_half2(g[8 * q + 4], g[8 * q + 5]),
-                             pack_half2(g[8 * q + 6], g[8 * q + 7]));
-              }
-            }
-          }
-          stash_store(kStashG, act, 2 * kPanelBytes128);
-          if (valid) {
-            float4 o;
-            o.x = 1.f / (1.f + expf(-a0));
-            o.y = 1.f / (1.f + expf(-a1));
-            o.z = 1.f / (1.f + expf(-a2));
-            o.w = sigma;
-            p.rgbsigma[e] = o;
-          }
-          // the accumulator has been drained; the arrive that releases it is the next tile's prologue
-          tc_fence_before();
+          if (kTrain && relu) mask_dst[c >> 1] = make_uint2(m0, m1);
         }
+        if (dens_stage) {
+          float raw = dens + __ldg(p.params + L::kBS);
+          if (p.noise != nullptr && valid) raw += __ldg(p.noise + e);
+          sigma = fmaxf(raw, 0.f);
+        }
+        if (st == 8) {
+          // direction encoding -> enc panel (the x encoding was last read by stage 5)
+          float vals[64];
+          vals[0] = vdx;
+          vals[1] = vdy;
+          vals[2] = vdz;
+          encode_axis(vdx, 4, vals + 3);
+          encode_axis(vdy, 4, vals + 11);
+          encode_axis(vdz, 4, vals + 19);
+#pragma unroll
+          for (int j = 27; j < 64; ++j) vals[j] = 0.f;
+          write_row_panel(enc, row, vals);
+          stash_store(kStashDir, enc, kPanelBytes128);
+        }
+        stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_a_ready + 8 * slot);
+      }
+      // ---------------- stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores ----------------
+      {
+        float a0 = __ldg(p.params + L::kBC1 + 0), a1 = __ldg(p.params + L::kBC1 + 1), a2 = __ldg(p.params + L::kBC1 + 2);
+        float4 b4[8], w0[8], w1[8], w2[8];
+        load8(b4, p.params + L::kBC0);
+        load8(w0, p.params + L::kWC1);
+        load8(w1, p.params + L::kWC1 + 128);
+        load8(w2, p.params + L::kWC1 + 256);
+        NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
+        acc_phase ^= 1;
+        tc_fence_after();
+        stash_drain();  // the F image store reads act, which receives g below
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + c0, v);
+          tmem_ld_wait32(v);
+          uint32_t w[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float g0 = fmaxf(__uint_as_float(v[4 * q + 0]) + b4[q].x, 0.f);
+            const float g1 = fmaxf(__uint_as_float(v[4 * q + 1]) + b4[q].y, 0.f);
+            const float g2 = fmaxf(__uint_as_float(v[4 * q + 2]) + b4[q].z, 0.f);
+            const float g3 = fmaxf(__uint_as_float(v[4 * q + 3]) + b4[q].w, 0.f);
+            a0 = fmaf(g0, w0[q].x, fmaf(g1, w0[q].y, fmaf(g2, w0[q].z, fmaf(g3, w0[q].w, a0))));
+            a1 = fmaf(g0, w1[q].x, fmaf(g1, w1[q].y, fmaf(g2, w1[q].z, fmaf(g3, w1[q].w, a1))));
+            a2 = fmaf(g0, w2[q].x, fmaf(g1, w2[q].y, fmaf(g2, w2[q].z, fmaf(g3, w2[q].w, a2))));
+            w[2 * q] = pack_half2(g0, g1);
+            w[2 * q + 1] = pack_half2(g2, g3);
+          }
+          if (c0 + 32 < 128) {  // next chunk's constants (L1-resident after the first tile)
+            load8(b4, p.params + L::kBC0 + c0 + 32);
+            load8(w0, p.params + L::kWC1 + c0 + 32);
+            load8(w1, p.params + L::kWC1 + 128 + c0 + 32);
+            load8(w2, p.params + L::kWC1 + 256 + c0 + 32);
+          }
+          if (kTrain) {
+            const uint32_t base = act + (c0 >> 6) * kPanelBytes128 + row_off;
+            const uint32_t ch0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(base + ((((ch0 + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          }
+        }
+        stash_store(kStashG, act, 2 * kPanelBytes128);
+        if (valid) {
+          float4 o;
+          o.x = 1.f / (1.f + expf(-a0));
+          o.y = 1.f / (1.f + expf(-a1));
+          o.z = 1.f / (1.f + expf(-a2));
+          o.w = sigma;
+          p.rgbsigma[e] = o;
+        }
+        // the accumulator has been drained; the arrive that releases it is the next tile's prologue
+        tc_fence_before();
       }
     }
     if (kTrain && tg == 0) bulk_wait_all<0>();
@@ -446,6 +520,7 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
   NERF_CHECK_ARG(n_evals < (int64_t(1) << 31) - kTile, "mlp_forward: n_rays*n_samples must be < 2^31 per call");
   NERF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0 && (reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0,
                  "mlp_forward: packed must be 128-byte and rgbsigma 16-byte aligned");
+  NERF_CHECK_ARG((reinterpret_cast<uintptr_t>(params) & 15) == 0, "mlp_forward: params must be 16-byte aligned");
   NERF_CHECK_ARG(stash == nullptr || (reinterpret_cast<uintptr_t>(stash) & 127) == 0, "mlp_forward: stash must be 128-byte aligned");
   FwdParams p;
   p.rgbsigma = reinterpret_cast<float4*>(rgbsigma);

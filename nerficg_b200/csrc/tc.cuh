@@ -131,6 +131,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// wait for outstanding tcgen05.ld AND pin the destination registers behind the wait: the "+r" operands stop the
+// compiler from hoisting arithmetic on r[] above the wait (the load itself only names them as outputs)
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// register reallocation between warp roles (whole warpgroups): producer / MMA warps give registers to the epilogues
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- UMMA descriptors ---------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -184,6 +206,15 @@ __device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 0xFFFF in each 16-bit half whose fp16 value is > 0 (one HSET2.BM)
+__device__ __forceinline__ uint32_t half2_gt0_mask(uint32_t w) {
+  const __half2 z = __floats2half2_rn(0.f, 0.f);
+  return __hgt2_mask(*reinterpret_cast<__half2*>(&w), z);
+}
+// ReLU mask bit layout used by the forward stash and the dgrad chain: within a 32-column chunk, column j is bit
+// (j >> 1) + 16 * (j & 1), i.e. the packed half2 word q = j >> 1 contributes bits q (low half) and 16 + q (high half).
+__host__ __device__ __forceinline__ uint32_t relu_mask_bit(uint32_t j) { return (j >> 1) + ((j & 1u) << 4); }
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
