@@ -121,6 +121,8 @@ int nerf_debug_set_timing(void* device_buffer);
  * D[128][n] = A[128][k] * B[n][k]^T with operand images built on device; mode selects the
  * descriptor flavour (0: K-major fp16, 1: MN-major operands as in wgrad, 2: K-major bf16). */
 int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream);
+/* CTA-pair flavour (cta_group::2, one 2-CTA cluster): D[256][n] = A[256][k] * B[n][k]^T, K-major fp16. */
+int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,14 +19,13 @@ using namespace tc;
 
 namespace bwd {
 constexpr int kThreads = 384;
-constexpr int kRingStages = 6;                           // 16 KB stages (64 inputs x 128 outputs), see mlp_fwd.cu
+constexpr int kRingStages = 6;                           // 16 KB stages: this CTA's 128-column half of one W^T panel (mlp_fwd.cu)
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 constexpr uint32_t kSlotBytes = kActBytes;
 constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
-static_assert(kRingStages % 2 == 0, "ring stages are consumed in pairs");
 constexpr int kRegsEpilogue = 232, kRegsOther = 40;
 }  // namespace bwd
 
@@ -76,7 +75,7 @@ __device__ __forceinline__ void dgrad_chunk(const uint32_t (&v)[32], uint32_t m,
                  w[4 * q + 2], w[4 * q + 3]);
 }
 
-__global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
   using namespace bwd;
   using L = ParamLayout;
   extern __shared__ uint8_t smem_raw[];
@@ -84,44 +83,47 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
   const uint32_t bars = smem_base + kOffBars;
   const uint32_t bar_w_full = bars;
   const uint32_t bar_w_empty = bars + 8 * kRingStages;
-  const uint32_t bar_a_ready = bars + 16 * kRingStages;
+  const uint32_t bar_w_peer = bars + 16 * kRingStages;  // leader only: the peer's half of the ring stage has landed
+  const uint32_t bar_a_ready = bars + 24 * kRingStages;  // leader only: both CTAs' operands written
   const uint32_t bar_acc_ready = bar_a_ready + 16;
-  const uint32_t bar_load = bar_acc_ready + 16;  // [2] G image landed in shared memory
-  const uint32_t tmem_slot = bar_load + 16;
+  const uint32_t tmem_slot = bar_acc_ready + 16;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the cta_group::2 pair (see mlp_fwd.cu)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) {
       mbar_init(bar_w_full + 8 * i, 1);
       mbar_init(bar_w_empty + 8 * i, 1);
+      mbar_init(bar_w_peer + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_a_ready + 8 * s, 128);
+      mbar_init(bar_a_ready + 8 * s, 8);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
-      mbar_init(bar_load + 8 * s, 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int pairs_total = (p.n_tiles + 1) / 2;
-  const int n_iters = (pairs_total + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+  const int n_clusters = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+  const int n_groups = (p.n_tiles + 1) / 2;  // group = 256 samples = one tile per CTA of the pair
+  const int n_iters = ((n_groups + 1) / 2 + n_clusters - 1) / n_clusters;
+  auto group_of = [&](int it, int slot) { return (it * n_clusters + cluster_id) * 2 + slot; };
+  auto active = [&](int it, int slot) { return group_of(it, slot) < n_groups; };
   const uint8_t* wimg = p.packed + kBwdImageOffset;
 
   const bool prof_on = p.prof != nullptr;
   if (warp < 4) {
     setmaxnreg_dec<kRegsOther>();
     if (warp == 0) {
-      // weight producer: K' panel pp of stage st -> ring stages (2j, 2j+1) = the two 128-column halves of W^T
+      // weight producer: rows [128 * rank, +128) (output columns of dX) of every W^T panel -> one ring stage
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
       long long t_wait = 0;
@@ -129,14 +131,14 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(it, slot) >= p.n_tiles) continue;
+            if (!active(it, slot)) continue;
             const int first = bwd_first_panel(st), np = bwd_panels(st);
-            for (int j = 0; j < 2 * np; ++j) {
+            for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
-                              wimg + (uint32_t)(first + (j >> 1)) * kPanelBytes256 + (j & 1) * kRingStageBytes, kRingStageBytes,
+                              wimg + (uint32_t)(first + pp) * kPanelBytes256 + rank * kRingStageBytes, kRingStageBytes,
                               bar_w_full + 8 * stage, keep);
               }
               __syncwarp();
@@ -150,39 +152,37 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         atomicAdd(p.prof + 13, (unsigned long long)t_wait);
         atomicAdd(p.prof + 14, (unsigned long long)(clock64() - t_begin));
       }
-    } else if (warp == 1) {
-      // MMA issuer: warp-uniform loop, one elected lane issues N = 256 instructions (see mlp_fwd.cu)
+    } else if (warp == 1 && rank == 0) {
+      // MMA issuer (leader CTA): warp-uniform loop, one elected lane issues cta_group::2 M=256 x N=256 instructions
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      constexpr uint32_t idesc = make_idesc(128, 256, kF16, kF16, 0, 0);
+      constexpr uint32_t idesc = make_idesc(256, 256, kF16, kF16, 0, 0);
       long long t_a = 0, t_w = 0;
       const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(it, slot) >= p.n_tiles) continue;
+            if (!active(it, slot)) continue;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            NERF_TIMED(prof_on, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
+            NERF_TIMED(prof_on, t_a, mbar_wait_cluster(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
-              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * (stage + 1), phase));
+              NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t da = make_smem_desc(act + pp * kPanelBytes128, 16u, kAtomBytes);
                 const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes, 16u, kAtomBytes);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
-                umma_commit(bar_w_empty + 8 * stage);
-                umma_commit(bar_w_empty + 8 * (stage + 1));
-                if (pp == np - 1) umma_commit(bar_acc_ready + 8 * slot);
+                for (int ks = 0; ks < 4; ++ks) umma2(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
+                umma_commit2(bar_w_empty + 8 * stage, 3);
+                if (pp == np - 1) umma_commit2(bar_acc_ready + 8 * slot, 3);
               }
               __syncwarp();
-              stage += 2;
-              if (stage == kRingStages) {
+              if (++stage == kRingStages) {
                 stage = 0;
                 phase ^= 1;
               }
@@ -194,6 +194,24 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         atomicAdd(p.prof + 12, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 19, 1ull);
       }
+    } else if (warp == 1) {
+      // relay (peer CTA): forwards "my half of ring stage s has landed" to the leader's issuer
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < n_iters; ++it)
+        for (int st = 0; st < kBwdStages; ++st)
+          for (int slot = 0; slot < 2; ++slot) {
+            if (!active(it, slot)) continue;
+            const int np = bwd_panels(st);
+            for (int pp = 0; pp < np; ++pp) {
+              mbar_wait(bar_w_full + 8 * stage, phase);
+              if (elect_one()) mbar_arrive_cluster(mapa(bar_w_peer + 8 * stage, 0));
+              __syncwarp();
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
     }
   } else {
     setmaxnreg_inc<kRegsEpilogue>();
@@ -205,22 +223,24 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;
     const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
-    uint32_t acc_phase = 0, load_phase = 0;
+    uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+    const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
     const bool prof = prof_on && tg == 0 && slot == 0;
     long long t_accw = 0, t_drain = 0, t_pro = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
-      const int tile = tile_of(it, slot);
-      if (tile >= p.n_tiles) break;
+      if (!active(it, slot)) break;
+      const int tile = group_of(it, slot) * 2 + (int)rank;
+      const bool tile_ok = tile < p.n_tiles;  // a peer without a tile still takes part in the pair's MMAs
       const int64_t e = (int64_t)tile * kTile + row;
-      const bool valid = e < p.n_evals;
+      const bool valid = tile_ok && e < p.n_evals;
 
       auto gstash_store = [&](int region, uint32_t src, uint32_t bytes) {
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (tg == 0) {
+        if (tg == 0 && tile_ok) {
           bulk_s2g_hint(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes,
                         l2_evict_first());
           bulk_commit();
@@ -237,12 +257,16 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
 
       // ---------------- prologue ----------------
       const long long t_tile = prof ? clock64() : 0;
-      gstash_drain();  // previous tile's D0 store still reads act
-      if (tg == 0) {   // G image (2 panels) -> act panels 2,3
-        mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
-        bulk_g2s_hint(act + 2 * kPanelBytes128,
-                      p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
-                      2 * kPanelBytes128, bar_load + 8 * slot, l2_evict_first());
+      // this row of the stashed G image (post-ReLU colour-layer activations, 128 x fp16), straight into registers:
+      // in flight while the previous tile's last image store drains (a bulk copy through shared memory exposed the
+      // whole HBM latency once per tile -- measured 7 K cycles of prologue per tile)
+      uint4 gq[16];
+      {
+        const uint8_t* gsrc = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          gq[q] = tile_ok ? __ldg(reinterpret_cast<const uint4*>(gsrc + (q >> 3) * kPanelBytes128 + panel_chunk_offset(row, q & 7)))
+                          : make_uint4(0, 0, 0, 0);
       }
       float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dsr = 0.f;
       if (valid) {
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         dp2 = dd.z * o.z * (1.f - o.z);
         dsr = dd.w;
       }
-      {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
+      if (tile_ok) {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
         uint8_t* hd = p.gstash + grad_region_offset(kGradHead, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(kGradHead);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -265,43 +289,31 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
           *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, ch)) = v;
         }
       }
-      mbar_wait(bar_load + 8 * slot, load_phase);
-      load_phase ^= 1;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float dg[32];
+      gstash_drain();  // previous tile's D0 store still reads act
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
-          const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
-          dg[4 * q + 0] = dp0 * w0.x + dp1 * w1.x + dp2 * w2.x;
-          dg[4 * q + 1] = dp0 * w0.y + dp1 * w1.y + dp2 * w2.y;
-          dg[4 * q + 2] = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
-          dg[4 * q + 3] = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
+      for (int q = 0; q < 16; ++q) {  // 8 columns per 16-byte chunk: dL/dg = W_c1^T dp, masked by g > 0
+        const float4 w0a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 8 * q)), w0b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 8 * q) + 1);
+        const float4 w1a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + 8 * q)), w1b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + 8 * q) + 1);
+        const float4 w2a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + 8 * q)), w2b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + 8 * q) + 1);
+        const float dg[8] = {dp0 * w0a.x + dp1 * w1a.x + dp2 * w2a.x, dp0 * w0a.y + dp1 * w1a.y + dp2 * w2a.y,
+                             dp0 * w0a.z + dp1 * w1a.z + dp2 * w2a.z, dp0 * w0a.w + dp1 * w1a.w + dp2 * w2a.w,
+                             dp0 * w0b.x + dp1 * w1b.x + dp2 * w2b.x, dp0 * w0b.y + dp1 * w1b.y + dp2 * w2b.y,
+                             dp0 * w0b.z + dp1 * w1b.z + dp2 * w2b.z, dp0 * w0b.w + dp1 * w1b.w + dp2 * w2b.w};
+        const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+        uint32_t outw[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
+          const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
+          outw[t] = pack_half2(lo ? dg[2 * t] : 0.f, hi ? dg[2 * t + 1] : 0.f);
         }
-        const uint32_t gpanel = act + (2 + (c0 >> 6)) * kPanelBytes128;
-        const uint32_t dpanel = act + (c0 >> 6) * kPanelBytes128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = panel_chunk_offset(row, ((c0 & 63) >> 3) + q);
-          uint32_t g0, g1, g2, g3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(gpanel + off));
-          const uint32_t gw[4] = {g0, g1, g2, g3};
-          uint32_t outw[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
-            const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
-            outw[t] = pack_half2(lo ? dg[8 * q + 2 * t] : 0.f, hi ? dg[8 * q + 2 * t + 1] : 0.f);
-          }
-          st_shared_v4(dpanel + off, outw[0], outw[1], outw[2], outw[3]);
-        }
+        st_shared_v4(act + (q >> 3) * kPanelBytes128 + panel_chunk_offset(row, q & 7), outw[0], outw[1], outw[2], outw[3]);
       }
       gstash_store(kGradC0, act, 2 * kPanelBytes128);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_a_ready + 8 * slot);
+      __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
 
       // ---------------- chain stages ----------------
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
         const int mask_layer = 8 - st;  // valid for st >= 1
         uint4 mk0 = make_uint4(~0u, ~0u, ~0u, ~0u), mk1 = mk0;
-        if (st >= 1) {  // ReLU masks of the whole row (8 words), in flight while the MMAs still run
+        if (st >= 1 && tile_ok) {  // ReLU masks of the whole row (8 words), in flight while the MMAs still run
           const uint4* mp = reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32));
           mk0 = __ldg(mp);
           mk1 = __ldg(mp + 1);
@@ -340,7 +352,8 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
         if (st < kBwdStages - 1) {
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(bar_a_ready + 8 * slot);
+          __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
         } else {
           tc_fence_before();  // accumulator drained; released by the next tile's prologue arrive
         }
@@ -355,8 +368,8 @@ __global__ void __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdPa
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
 int launch_wgrad(float* grads, const uint8_t* stash, const uint8_t* gstash, int n_tiles, float inv_scale, cudaStream_t stream);
@@ -397,8 +410,8 @@ static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbs
       NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
       attr_set = true;
     }
-    const int pairs = (p.n_tiles + 1) / 2;
-    const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+    const int group_pairs = ((p.n_tiles + 1) / 2 + 1) / 2;  // one cluster iteration = 2 slots x 2 tiles
+    const int grid = 2 * (group_pairs < kNumSMs / 2 ? group_pairs : kNumSMs / 2);
     mlp_dgrad_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
     NERF_CHECK_LAUNCH("mlp_dgrad_kernel");
   }

@@ -1,14 +1,17 @@
 // mlp_fwd.cu -- K3: positional encoding + the 8x256 skip-connected NeRF MLP as ONE fused,
 // persistent, warp-specialised tcgen05 kernel.
 //
-// A CTA owns one SM and walks pairs of 128-sample tiles ("slots" 0/1) through the whole 10-stage
-// chain (mlp_layout.cuh) without touching HBM in between:
-//   warp 0      weight producer: streams fp16 weight panels (pre-swizzled UMMA images) from L2
-//               into a shared-memory ring with 1-D bulk copies (TMA engine) + mbarriers
-//   warp 1      MMA issuer: the warp runs the loop uniformly and ONE elected lane issues
-//               tcgen05.mma (M=128, N=256, K=16) from the slot's activation panels (A, shared
-//               memory) and a PAIR of ring stages (B: both 128-neuron halves of one K panel);
-//               accumulators live in TMEM (2 slots x 256 fp32 columns = all 512 columns)
+// Two CTAs on the two SMs of a TPC form a cluster and work as a cta_group::2 PAIR: each CTA owns 128 samples of
+// a 256-sample "group" per slot, and walks two groups ("slots" 0/1) through the whole 10-stage chain
+// (mlp_layout.cuh) without touching HBM in between:
+//   warp 0      weight producer: streams THIS CTA's HALF of every fp16 weight panel (pre-swizzled UMMA images,
+//               128 of the 256 neurons) from L2 into a shared-memory ring with 1-D bulk copies + mbarriers
+//   warp 1      leader CTA: MMA issuer -- the warp runs the loop uniformly and ONE elected lane issues
+//               tcgen05.mma.cta_group::2 (M=256, N=256, K=16): rows 0..127 from its own activation panels
+//               and TMEM, rows 128..255 from the peer's, B = the two CTAs' ring stages (one half each), so a
+//               weight byte is fetched once per 256 samples; completion is multicast to both CTAs' barriers.
+//               peer CTA: relay -- forwards "my half of ring stage s has landed" to the leader's barrier.
+//               accumulators live in TMEM (2 slots x 256 fp32 columns = all 512 columns, in each CTA)
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue of slot 0 \  tcgen05.ld accumulator -> +bias, ReLU -> fp16 -> swizzled
 //   warps 8-11  epilogue of slot 1 /  A-operand panels of the next stage (in place); the two slots
@@ -19,6 +22,9 @@
 // memory, region-major, see mlp_layout.cuh) and per-layer ReLU bit masks.
 //
 // Measured lessons baked into the structure (DESIGN.md "K3"):
+//   * one CTA per tile pair was weight-starved: 128 KB of weights per 128 samples and layer is 64 B/cycle/SM at
+//     tensor peak (18 TB/s chip-wide) and the MMA issuer spent 24-40 % of its time waiting for ring stages; the
+//     CTA pair halves both the L2 -> SM stream and the shared-memory reads of B;
 //   * the issuing warp must stay warp-uniform with elect.sync around the tcgen05 instructions: issued under
 //     `if (lane == 0)` every MMA was wrapped in a compiler-generated ELECT/BRA.U.ANY waterfall and cost ~190
 //     cycles of issue for 64 cycles of tensor work;
@@ -35,8 +41,7 @@ using namespace tc;
 
 namespace fwd {
 constexpr int kThreads = 384;
-// weight ring: 16 KB stages = one K panel (64 inputs) x 128 output neurons, consumed in PAIRS (stage 2j, 2j+1 are
-// adjacent in shared memory, so a pair is one 256-neuron B operand).
+// weight ring: 16 KB stages = one K panel (64 inputs) x this CTA's 128 output neurons (64 for the colour layer)
 constexpr int kRingStages = 4;
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 // shared memory map (offsets from the 1024-aligned base)
@@ -45,7 +50,6 @@ constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;  // + barriers + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
-static_assert(kRingStages % 2 == 0, "ring stages are consumed in pairs");
 constexpr int kRegsEpilogue = 232, kRegsOther = 40;  // 256 * 232 + 128 * 40 = 64512 <= 65536
 }  // namespace fwd
 
@@ -135,7 +139,7 @@ __device__ __forceinline__ uint32_t hidden_chunk(const uint32_t (&v)[32], const 
 }
 
 template <bool kTrain>
-__global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   using namespace fwd;
   using L = ParamLayout;
   extern __shared__ uint8_t smem_raw[];
@@ -144,44 +148,49 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
   // barrier map (8 bytes each)
   const uint32_t bar_w_full = bars;                       // [kRingStages]
   const uint32_t bar_w_empty = bars + 8 * kRingStages;    // [kRingStages]
-  const uint32_t bar_a_ready = bars + 16 * kRingStages;   // [2] operand of the next stage written + accumulator drained
-  const uint32_t bar_acc_ready = bar_a_ready + 16;        // [2] accumulator complete
+  const uint32_t bar_w_peer = bars + 16 * kRingStages;    // [kRingStages] leader only: the peer's half of the stage has landed
+  const uint32_t bar_a_ready = bars + 24 * kRingStages;   // [2] leader only: operands of BOTH CTAs written + accumulators drained
+  const uint32_t bar_acc_ready = bar_a_ready + 16;        // [2] accumulator complete (multicast commit)
   const uint32_t tmem_slot = bar_acc_ready + 16;          // uint32: TMEM base address
+  const uint32_t rank = cluster_ctarank();                // 0 = leader
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) {
       mbar_init(bar_w_full + 8 * i, 1);
       mbar_init(bar_w_empty + 8 * i, 1);
+      mbar_init(bar_w_peer + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_a_ready + 8 * s, 128);
+      mbar_init(bar_a_ready + 8 * s, 8);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int pairs_total = (p.n_tiles + 1) / 2;
-  const int n_iters = (pairs_total + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int it, int slot) { return (it * (int)gridDim.x + (int)blockIdx.x) * 2 + slot; };
+  // group = 256 samples = one tile per CTA of the pair; a cluster handles two groups (slots) per iteration
+  const int n_clusters = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+  const int n_groups = (p.n_tiles + 1) / 2;
+  const int n_iters = ((n_groups + 1) / 2 + n_clusters - 1) / n_clusters;
+  auto group_of = [&](int it, int slot) { return (it * n_clusters + cluster_id) * 2 + slot; };
+  auto active = [&](int it, int slot) { return group_of(it, slot) < n_groups; };  // identical in both CTAs
   const bool prof_on = p.prof != nullptr;
 
   if (warp < 4) {
     setmaxnreg_dec<kRegsOther>();
     if (warp == 0) {
       // =============================== weight producer ===============================
-      // Every (stage, slot) consumes an even number of ring stages.  Stages 0..8: K panel pp -> ring stages
-      // (2j, 2j+1) = neuron halves 0 / 1.  Stage 9 (128 neurons): ring pair = K panels (2j, 2j+1); the 6th,
-      // non-existent panel is a zero-byte stage (plain arrive) so the pairing never shifts.
+      // one ring stage per K panel: rows [128 * rank, +128) of the 256-neuron panels, [64 * rank, +64) of the
+      // 128-neuron colour-layer panels (the cta_group::2 MMA takes the other half from the peer's ring)
       uint32_t stage = 0, phase = 0;
       const uint64_t keep = l2_evict_last();
       long long t_wait = 0;
@@ -189,20 +198,15 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(it, slot) >= p.n_tiles) continue;
-            const int first = fwd_first_panel(st);
-            const int n_stage_loads = st == 9 ? 6 : 2 * fwd_panels(st);
-            for (int j = 0; j < n_stage_loads; ++j) {
+            if (!active(it, slot)) continue;
+            const int first = fwd_first_panel(st), np = fwd_panels(st);
+            const uint32_t bytes = st == 9 ? kRingStageBytes / 2 : kRingStageBytes;  // colour layer: 64 of 128 neurons
+            for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
               if (elect_one()) {
-                if (st == 9 && j == 5) {
-                  mbar_arrive(bar_w_full + 8 * stage);
-                } else {
-                  const uint8_t* src = st == 9 ? p.packed + fwd_panel_offset(first + j)
-                                               : p.packed + fwd_panel_offset(first + (j >> 1)) + (j & 1) * kRingStageBytes;
-                  mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
-                  bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes, src, kRingStageBytes, bar_w_full + 8 * stage, keep);
-                }
+                mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
+                bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes, p.packed + fwd_panel_offset(first + pp) + rank * bytes, bytes,
+                              bar_w_full + 8 * stage, keep);
               }
               __syncwarp();
               if (++stage == kRingStages) {
@@ -217,58 +221,43 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
         atomicAdd(p.prof + 3, (unsigned long long)t_wait);
         atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
       }
-    } else if (warp == 1) {
-      // =============================== MMA issuer ===============================
+    } else if (warp == 1 && rank == 0) {
+      // =============================== MMA issuer (leader CTA) ===============================
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
-      constexpr uint32_t idesc256 = make_idesc(128, 256, kF16, kF16, 0, 0);
-      constexpr uint32_t idesc128 = make_idesc(128, 128, kF16, kF16, 0, 0);
+      constexpr uint32_t idesc256 = make_idesc(256, 256, kF16, kF16, 0, 0);
+      constexpr uint32_t idesc128 = make_idesc(256, 128, kF16, kF16, 0, 0);
       long long t_a = 0, t_w = 0;
       const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(it, slot) >= p.n_tiles) continue;
+            if (!active(it, slot)) continue;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t enc = act + kActBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
-            NERF_TIMED(prof_on, t_a, mbar_wait(bar_a_ready + 8 * slot, a_phase[slot]));
+            NERF_TIMED(prof_on, t_a, mbar_wait_cluster(bar_a_ready + 8 * slot, a_phase[slot]));
             a_phase[slot] ^= 1;
             tc_fence_after();
-            const int n_steps = st == 9 ? 3 : fwd_panels(st);
-            for (int step = 0; step < n_steps; ++step) {
+            const int np = fwd_panels(st);
+            for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
-              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * (stage + 1), phase));
+              NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
               tc_fence_after();
-              const uint32_t ring = smem_base + kOffRing + stage * kRingStageBytes;
               if (elect_one()) {
-                if (st != 9) {
-                  // A: stage 0 reads the encoding panel; panel 4 of stage 5 is the retained encoding panel
-                  const uint64_t da = make_smem_desc((st == 0 || step == 4) ? enc : act + step * kPanelBytes128, 16u, kAtomBytes);
-                  const uint64_t db = make_smem_desc(ring, 16u, kAtomBytes);
+                // A: stage 0 reads the encoding panel; panel 4 of stages 5 / 9 is the encoding / direction panel
+                const uint64_t da = make_smem_desc((st == 0 || pp == 4) ? enc : act + pp * kPanelBytes128, 16u, kAtomBytes);
+                const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes, 16u, kAtomBytes);
+                const uint32_t idesc = st == 9 ? idesc128 : idesc256;
+                const int ksteps = (st == 9 && pp == 4) ? 2 : 4;  // the direction encoding is 32 wide
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc256, (step | ks) != 0);
-                } else {
-                  // two K panels of the 128-neuron colour layer per ring pair; panel 4 = direction encoding (32 wide)
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const int pp = 2 * step + h;
-                    if (pp < 5) {
-                      const uint64_t da = make_smem_desc(pp == 4 ? enc : act + pp * kPanelBytes128, 16u, kAtomBytes);
-                      const uint64_t db = make_smem_desc(ring + h * kRingStageBytes, 16u, kAtomBytes);
-#pragma unroll
-                      for (int ks = 0; ks < 4; ++ks)
-                        if (pp < 4 || ks < 2) umma(d_tmem, da + 2u * ks, db + 2u * ks, idesc128, (pp | ks) != 0);
-                    }
-                  }
-                }
-                umma_commit(bar_w_empty + 8 * stage);
-                umma_commit(bar_w_empty + 8 * (stage + 1));
-                if (step == n_steps - 1) umma_commit(bar_acc_ready + 8 * slot);
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < ksteps) umma2(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
+                umma_commit2(bar_w_empty + 8 * stage, 3);
+                if (pp == np - 1) umma_commit2(bar_acc_ready + 8 * slot, 3);
               }
               __syncwarp();
-              stage += 2;
-              if (stage == kRingStages) {
+              if (++stage == kRingStages) {
                 stage = 0;
                 phase ^= 1;
               }
@@ -282,6 +271,26 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 9, 1ull);
       }
+    } else if (warp == 1) {
+      // =============================== relay (peer CTA) ===============================
+      // tells the leader's issuer that this CTA's half of ring stage s has landed (bulk copies can only signal a
+      // barrier of their own CTA, and mbarriers cannot be waited on remotely)
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < n_iters; ++it)
+        for (int st = 0; st < kFwdStages; ++st)
+          for (int slot = 0; slot < 2; ++slot) {
+            if (!active(it, slot)) continue;
+            const int np = fwd_panels(st);
+            for (int pp = 0; pp < np; ++pp) {
+              mbar_wait(bar_w_full + 8 * stage, phase);
+              if (elect_one()) mbar_arrive_cluster(mapa(bar_w_peer + 8 * stage, 0));
+              __syncwarp();
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
     }
   } else {
     // =============================== epilogue warpgroups ===============================
@@ -297,16 +306,18 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
     uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+    const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);  // both CTAs announce their operands to the leader
     const bool prof = prof_on && tg == 0 && slot == 0;
     long long t_accw = 0, t_drain = 0, t_pro = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
-      const int tile = tile_of(it, slot);
-      if (tile >= p.n_tiles) break;
+      if (!active(it, slot)) break;
+      const int tile = group_of(it, slot) * 2 + (int)rank;
+      const bool tile_ok = tile < p.n_tiles;  // the last group may have no tile for the peer: it still takes part in the MMAs
       const long long t_tile = prof ? clock64() : 0;
       const int64_t e = (int64_t)tile * kTile + row;  // sample index
-      const bool valid = e < p.n_evals;
+      const bool valid = tile_ok && e < p.n_evals;
       const int ray = valid ? (int)(e / p.n_samples) : 0;
 
       // stash helper: one thread bulk-stores an image from shared memory after the group fenced its writes
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
         if (kTrain) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
-          if (tg == 0) {
+          if (tg == 0 && tile_ok) {
             bulk_s2g_hint(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes,
                           l2_evict_first());
             bulk_commit();
@@ -358,7 +369,8 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
       stash_store(kStashEnc, enc, kPanelBytes128);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_a_ready + 8 * slot);
+      __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
 
       float sigma = 0.f;
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
         stash_drain();  // the act image of the previous stage may still be being stored
         float dens = 0.f;
         uint2* mask_dst = nullptr;
-        if (kTrain && relu)
+        if (kTrain && relu && tile_ok)
           mask_dst = reinterpret_cast<uint2*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
                                               (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
 #pragma unroll 1
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
             m1 = dens_stage ? hidden_chunk<true>(v, bb, wb, relu, base, 4, row, dens)
                             : hidden_chunk<false>(v, bb, wb, relu, base, 4, row, dens);
           }
-          if (kTrain && relu) mask_dst[c >> 1] = make_uint2(m0, m1);
+          if (mask_dst != nullptr) mask_dst[c >> 1] = make_uint2(m0, m1);
         }
         if (dens_stage) {
           float raw = dens + __ldg(p.params + L::kBS);
@@ -430,7 +442,8 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
         stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(bar_a_ready + 8 * slot);
+        __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       }
       // ---------------- stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores ----------------
       {
@@ -498,8 +511,8 @@ __global__ void __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdPara
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();  // the peer may still be reading this CTA's shared memory / arriving on its barriers
+  if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
 }  // namespace nerf
@@ -537,8 +550,8 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
   p.n_evals = n_evals;
   p.n_tiles = (int)((n_evals + kTile - 1) / kTile);
   p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
-  const int pairs = (p.n_tiles + 1) / 2;
-  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  const int group_pairs = ((p.n_tiles + 1) / 2 + 1) / 2;  // one cluster iteration = 2 slots x 2 tiles
+  const int grid = 2 * (group_pairs < kNumSMs / 2 ? group_pairs : kNumSMs / 2);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);

@@ -104,7 +104,84 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(float* __restrict__ ou
   if (tid < 32) tmem_dealloc(tmem, ncols);
 }
 
+// ---- CTA-pair flavour: D[256][n] = A[256][k] * B[n][k]^T with one cta_group::2 instruction stream ----------
+// CTA r of the 2-CTA cluster holds A rows [128r, 128r+128) and B rows [n/2 * r, n/2 * (r+1)); the leader issues
+// M = 256 MMAs, the peer announces its operands with a remote mbarrier arrive (the relay used by the MLP kernels)
+// and both CTAs are released by ONE multicast tcgen05.commit.  Checks the M / N split conventions of tc.cuh.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    selftest2_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_done, bar_peer;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int nh = n / 2;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + 128u * k * 2u;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_done), 1);
+    mbar_init(smem_u32(&bar_peer), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 256);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  for (int i = tid; i < 128 * k; i += 128) {
+    int r = i / k, c = i % k;
+    *reinterpret_cast<uint16_t*>(sa + (c / 64) * (128 * 128) + panel_offset(r, c % 64)) = to_bits(a[(size_t)(128 * rank + r) * k + c], false);
+  }
+  for (int i = tid; i < nh * k; i += 128) {
+    int r = i / k, c = i % k;
+    *reinterpret_cast<uint16_t*>(sb + (c / 64) * (nh * 128) + panel_offset(r, c % 64)) = to_bits(b[(size_t)(nh * rank + r) * k + c], false);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (rank == 1 && tid == 0) mbar_arrive_cluster(mapa(smem_u32(&bar_peer), 0));
+  if (rank == 0 && warp == 0) {
+    mbar_wait_cluster(smem_u32(&bar_peer), 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(256, n, kF16, kF16, 0, 0);
+      for (int ks = 0; ks < k / 16; ++ks)
+        umma2(tmem, desc_kmajor(smem_u32(sa) + (ks / 4) * (128 * 128), ks % 4), desc_kmajor(smem_u32(sb) + (ks / 4) * (nh * 128), ks % 4),
+              idesc, ks != 0);
+      umma_commit2(smem_u32(&bar_done), 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait_cluster(smem_u32(&bar_done), 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait32(v);
+    for (int j = 0; j < 32; ++j) out[(size_t)(128 * rank + row) * n + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+
 }  // namespace nerf
+
+extern "C" int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0, "selftest2: n must be a multiple of 64 in [64,256], got %d", n);
+  NERF_CHECK_ARG(k >= 64 && k <= 256 && k % 64 == 0, "selftest2: k must be a multiple of 64 in [64,256], got %d", k);
+  size_t smem = 1024 + size_t(128) * k * 2 + size_t(n / 2) * k * 2;
+  cudaError_t e = cudaFuncSetAttribute(selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  NERF_CHECK_ARG(e == cudaSuccess, "selftest2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  selftest2_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k);
+  NERF_CHECK_LAUNCH("selftest2_kernel");
+  return 0;
+}
 
 extern "C" int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream) {
   using namespace nerf;

@@ -147,3 +147,13 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     check(load().nerf_selftest_umma(ptr(out), ptr(a), ptr(b), b.shape[0], a.shape[1], mode, stream_ptr()),
           'nerf_selftest_umma')
     return out
+
+
+def selftest_umma2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """D = A @ B^T on one 256-row tile through a cta_group::2 CTA pair (tests only)."""
+    a, b = _f32c(a), _f32c(b)
+    require_device(a)
+    assert a.shape[0] == 256 and a.shape[1] == b.shape[1]
+    out = torch.empty((256, b.shape[0]), dtype=torch.float32, device=a.device)
+    check(load().nerf_selftest_umma2(ptr(out), ptr(a), ptr(b), b.shape[0], a.shape[1], stream_ptr()), 'nerf_selftest_umma2')
+    return out

@@ -212,24 +212,31 @@ def test_training_psnr_parity(fw):
         psnr_ref = O.psnr(ref['rgb'].clamp(0, 1), gt)
 
         # ---- CUDA path ----
-        model, renderer = _build(fw, sd0)
-        trainer = TRAINING_INSTANCE(model=model, renderer=renderer)
+        # The weight gradients are accumulated with fp32 atomics, so two trainings differ in the last bits and, this
+        # early in training (PSNR still climbing 0.1 dB per 10 steps), end +-0.03 dB apart (tools/psnr_spread.py).
+        # The bar is therefore applied to the mean of three runs; every run must stay within 0.1 dB.
         cam = ds.default_camera
-        for it in range(steps):
-            b = pool[ids[it]].to(device=torch.device(DEV))
-            noise = [{k: v.to(DEV) for k, v in draws[it].items()}]
-            out = renderer.render_rays(b, cam, randomize_samples=True, noise=noise)
-            trainer.loss(out, b, bg.to(DEV)).backward()
-            trainer.optimizer.step()
-            trainer.optimizer.zero_grad()
-            trainer.lr_scheduler.step()
-        with torch.no_grad():
-            got = renderer.render_rays(test.to(device=torch.device(DEV)), cam)
-        psnr_got = O.psnr(got['rgb'].cpu().clamp(0, 1), gt)
+        runs = []
+        for _ in range(3):
+            model, renderer = _build(fw, sd0)
+            trainer = TRAINING_INSTANCE(model=model, renderer=renderer)
+            for it in range(steps):
+                b = pool[ids[it]].to(device=torch.device(DEV))
+                noise = [{k: v.to(DEV) for k, v in draws[it].items()}]
+                out = renderer.render_rays(b, cam, randomize_samples=True, noise=noise)
+                trainer.loss(out, b, bg.to(DEV)).backward()
+                trainer.optimizer.step()
+                trainer.optimizer.zero_grad()
+                trainer.lr_scheduler.step()
+            with torch.no_grad():
+                got = renderer.render_rays(test.to(device=torch.device(DEV)), cam)
+            runs.append(O.psnr(got['rgb'].cpu().clamp(0, 1), gt))
+        psnr_got = sum(runs) / len(runs)
         import json, os
         os.makedirs('gpurun_out', exist_ok=True)
         with open('gpurun_out/psnr_parity.json', 'w') as f:
-            json.dump({'steps': steps, 'psnr_oracle_cpu': psnr_ref, 'psnr_cuda': psnr_got}, f)
+            json.dump({'steps': steps, 'psnr_oracle_cpu': psnr_ref, 'psnr_cuda_runs': runs, 'psnr_cuda_mean': psnr_got}, f)
+        assert all(abs(r - psnr_ref) <= 0.1 for r in runs), (runs, psnr_ref)
         assert psnr_ref > 12.0           # training actually progressed
         assert abs(psnr_got - psnr_ref) <= 0.05, (psnr_got, psnr_ref)
     finally:

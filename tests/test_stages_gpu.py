@@ -26,6 +26,16 @@ def test_umma_selftest(ops, mode, n, k):
     assert torch.allclose(out.double(), ref, rtol=1e-4, atol=1e-3), (out.double() - ref).abs().max()
 
 
+@pytest.mark.parametrize('n,k', [(256, 256), (128, 64), (64, 128), (256, 64)])
+def test_umma_cta_pair_selftest(ops, n, k):
+    g = torch.Generator().manual_seed(n + k)
+    a = torch.randn(256, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    ref = a.half().double() @ b.half().double().T
+    out = ops.selftest_umma2(a.to(DEV), b.to(DEV)).cpu()
+    assert torch.allclose(out.double(), ref, rtol=1e-4, atol=1e-3), (out.double() - ref).abs().max()
+
+
 def test_stratified_golden(ops, golden):
     g = golden('stratified')
     z = ops.sample_stratified(g['n'], g['nc'], g['near'], g['far'], g['u'].to(DEV), torch.device(DEV)).cpu()
