@@ -86,7 +86,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
   const uint32_t bar_w_peer = bars + 16 * kRingStages;  // leader only: the peer's half of the ring stage has landed
   const uint32_t bar_a_ready = bars + 24 * kRingStages;  // leader only: both CTAs' operands written
   const uint32_t bar_acc_ready = bar_a_ready + 16;
-  const uint32_t tmem_slot = bar_acc_ready + 16;
+  const uint32_t bar_load = bar_acc_ready + 16;  // [2] G image landed in shared memory
+  const uint32_t tmem_slot = bar_load + 16;
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the cta_group::2 pair (see mlp_fwd.cu)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,6 +100,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_a_ready + 8 * s, 8);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
+      mbar_init(bar_load + 8 * s, 1);
     }
     fence_barrier_init();
   }
@@ -223,7 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;
     const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, load_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
     const bool prof = prof_on && tg == 0 && slot == 0;
@@ -257,16 +259,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
 
       // ---------------- prologue ----------------
       const long long t_tile = prof ? clock64() : 0;
-      // this row of the stashed G image (post-ReLU colour-layer activations, 128 x fp16), straight into registers:
-      // in flight while the previous tile's last image store drains (a bulk copy through shared memory exposed the
-      // whole HBM latency once per tile -- measured 7 K cycles of prologue per tile)
-      uint4 gq[16];
-      {
-        const uint8_t* gsrc = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG);
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          gq[q] = tile_ok ? __ldg(reinterpret_cast<const uint4*>(gsrc + (q >> 3) * kPanelBytes128 + panel_chunk_offset(row, q & 7)))
-                          : make_uint4(0, 0, 0, 0);
+      gstash_drain();  // previous tile's D0 store still reads act
+      if (tg == 0) {   // G image (2 panels) -> act panels 2,3
+        if (tile_ok) {
+          mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
+          bulk_g2s_hint(act + 2 * kPanelBytes128,
+                        p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
+                        2 * kPanelBytes128, bar_load + 8 * slot, l2_evict_first());
+        } else {
+          mbar_arrive(bar_load + 8 * slot);  // nothing to load: whatever the panels hold is multiplied by zero gradients
+        }
       }
       float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dsr = 0.f;
       if (valid) {
@@ -289,25 +291,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, ch)) = v;
         }
       }
-      gstash_drain();  // previous tile's D0 store still reads act
+      mbar_wait(bar_load + 8 * slot, load_phase);
+      load_phase ^= 1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float dg[32];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {  // 8 columns per 16-byte chunk: dL/dg = W_c1^T dp, masked by g > 0
-        const float4 w0a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 8 * q)), w0b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 8 * q) + 1);
-        const float4 w1a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + 8 * q)), w1b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + 8 * q) + 1);
-        const float4 w2a = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + 8 * q)), w2b = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + 8 * q) + 1);
-        const float dg[8] = {dp0 * w0a.x + dp1 * w1a.x + dp2 * w2a.x, dp0 * w0a.y + dp1 * w1a.y + dp2 * w2a.y,
-                             dp0 * w0a.z + dp1 * w1a.z + dp2 * w2a.z, dp0 * w0a.w + dp1 * w1a.w + dp2 * w2a.w,
-                             dp0 * w0b.x + dp1 * w1b.x + dp2 * w2b.x, dp0 * w0b.y + dp1 * w1b.y + dp2 * w2b.y,
-                             dp0 * w0b.z + dp1 * w1b.z + dp2 * w2b.z, dp0 * w0b.w + dp1 * w1b.w + dp2 * w2b.w};
-        const uint32_t gw[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
-        uint32_t outw[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
-          const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
-          outw[t] = pack_half2(lo ? dg[2 * t] : 0.f, hi ? dg[2 * t + 1] : 0.f);
+        for (int q = 0; q < 8; ++q) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
+          dg[4 * q + 0] = dp0 * w0.x + dp1 * w1.x + dp2 * w2.x;
+          dg[4 * q + 1] = dp0 * w0.y + dp1 * w1.y + dp2 * w2.y;
+          dg[4 * q + 2] = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
+          dg[4 * q + 3] = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
         }
-        st_shared_v4(act + (q >> 3) * kPanelBytes128 + panel_chunk_offset(row, q & 7), outw[0], outw[1], outw[2], outw[3]);
+        const uint32_t gpanel = act + (2 + (c0 >> 6)) * kPanelBytes128;
+        const uint32_t dpanel = act + (c0 >> 6) * kPanelBytes128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = panel_chunk_offset(row, ((c0 & 63) >> 3) + q);
+          uint32_t g0, g1, g2, g3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(gpanel + off));
+          const uint32_t gw[4] = {g0, g1, g2, g3};
+          uint32_t outw[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
+            const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
+            outw[t] = pack_half2(lo ? dg[8 * q + 2 * t] : 0.f, hi ? dg[8 * q + 2 * t + 1] : 0.f);
+          }
+          st_shared_v4(dpanel + off, outw[0], outw[1], outw[2], outw[3]);
+        }
       }
       gstash_store(kGradC0, act, 2 * kPanelBytes128);
       fence_proxy_async_smem();
@@ -315,6 +330,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
       if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
+      // pull the next tile's prologue inputs (upstream gradients, outputs, G image) into L2 while this tile's chain runs:
+      // the prologue otherwise exposes a full HBM round trip per tile
+      if (it + 1 < n_iters && active(it + 1, slot)) {
+        const int next = group_of(it + 1, slot) * 2 + (int)rank;
+        if (next < p.n_tiles) {
+          const int64_t en = (int64_t)next * kTile + row;
+          if (en < p.n_evals) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_rgbsigma + en));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rgbsigma + en));
+          }
+          const uint8_t* gn = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashG) + tg * 256;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + 128));
+        }
+      }
 
       // ---------------- chain stages ----------------
 #pragma unroll 1
@@ -328,25 +358,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           mk1 = __ldg(mp + 1);
         }
         const bool sig_stage = st == 1;  // dL/dh7 also receives dsigma_raw * w_sigma
-        float4 wa[8], wb[8];
-        if (sig_stage) load8(wa, p.params + L::kWS);
+        float4 wsv[8];
+        if (sig_stage) load8(wsv, p.params + L::kWS);
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         gstash_drain();                 // previous image store still reads act
         const uint32_t mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_acc, va);
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
-          uint32_t v[32];
           const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-          tmem_ld32(t_acc + 32 * c, v);
-          if (sig_stage) load8(wb, p.params + L::kWS + 32 * (c + 1));
-          tmem_ld_wait32(v);
-          if (sig_stage) dgrad_chunk<true>(v, mk[c], wa, dsr, base, 0, row); else dgrad_chunk<false>(v, mk[c], wa, dsr, base, 0, row);
-          tmem_ld32(t_acc + 32 * (c + 1), v);
-          if (sig_stage && c + 2 < 8) load8(wa, p.params + L::kWS + 32 * (c + 2));
-          tmem_ld_wait32(v);
-          if (sig_stage) dgrad_chunk<true>(v, mk[c + 1], wb, dsr, base, 4, row); else dgrad_chunk<false>(v, mk[c + 1], wb, dsr, base, 4, row);
+          tmem_ld_wait32(va);
+          tmem_ld32(t_acc + 32 * (c + 1), vb);
+          if (sig_stage) {
+            dgrad_chunk<true>(va, mk[c], wsv, dsr, base, 0, row);
+            load8(wsv, p.params + L::kWS + 32 * (c + 1));
+          } else {
+            dgrad_chunk<false>(va, mk[c], wsv, dsr, base, 0, row);
+          }
+          tmem_ld_wait32(vb);
+          if (c + 2 < 8) tmem_ld32(t_acc + 32 * (c + 2), va);
+          if (sig_stage) {
+            dgrad_chunk<true>(vb, mk[c + 1], wsv, dsr, base, 4, row);
+            if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
+          } else {
+            dgrad_chunk<false>(vb, mk[c + 1], wsv, dsr, base, 4, row);
+          }
         }
         gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
         if (st < kBwdStages - 1) {

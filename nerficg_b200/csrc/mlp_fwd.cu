@@ -380,9 +380,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF);
         const bool relu = st < 8;
         const bool dens_stage = st == 7;
-        float4 ba[8], bb[8], wa[8], wb[8];
+        float4 ba[8], bb[8], wsv[8];
         load8(ba, bias);  // in flight while the MMAs of this stage still run
-        if (dens_stage) load8(wa, p.params + L::kWS);
+        if (dens_stage) load8(wsv, p.params + L::kWS);
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
@@ -392,33 +392,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         if (kTrain && relu && tile_ok)
           mask_dst = reinterpret_cast<uint2*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
                                               (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
+        if (!kTrain) {
+          // software pipeline over the eight 32-column chunks: the TMEM load and the bias of chunk c+1 are in flight
+          // while chunk c is processed (va/vb and ba/bb alternate)
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_acc, va);
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          uint32_t v[32];
-          uint32_t m0, m1;
-          // ---- chunk c: bias in ba (wa), prefetch chunk c+1 into bb (wb) ----
-          tmem_ld32(t_acc + 32 * c, v);
-          load8(bb, bias + 32 * (c + 1));
-          if (dens_stage) load8(wb, p.params + L::kWS + 32 * (c + 1));
-          tmem_ld_wait32(v);
-          {
+          for (int c = 0; c < 8; c += 2) {
             const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-            m0 = dens_stage ? hidden_chunk<true>(v, ba, wa, relu, base, 0, row, dens)
-                            : hidden_chunk<false>(v, ba, wa, relu, base, 0, row, dens);
+            tmem_ld_wait32(va);
+            tmem_ld32(t_acc + 32 * (c + 1), vb);
+            load8(bb, bias + 32 * (c + 1));
+            if (dens_stage) {
+              hidden_chunk<true>(va, ba, wsv, relu, base, 0, row, dens);
+              load8(wsv, p.params + L::kWS + 32 * (c + 1));
+            } else {
+              hidden_chunk<false>(va, ba, wsv, relu, base, 0, row, dens);
+            }
+            tmem_ld_wait32(vb);
+            if (c + 2 < 8) {
+              tmem_ld32(t_acc + 32 * (c + 2), va);
+              load8(ba, bias + 32 * (c + 2));
+            }
+            if (dens_stage) {
+              hidden_chunk<true>(vb, bb, wsv, relu, base, 4, row, dens);
+              if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
+            } else {
+              hidden_chunk<false>(vb, bb, wsv, relu, base, 4, row, dens);
+            }
           }
-          // ---- chunk c+1: bias in bb (wb), prefetch chunk c+2 into ba (wa) ----
-          tmem_ld32(t_acc + 32 * (c + 1), v);
-          if (c + 2 < 8) {
-            load8(ba, bias + 32 * (c + 2));
-            if (dens_stage) load8(wa, p.params + L::kWS + 32 * (c + 2));
-          }
-          tmem_ld_wait32(v);
-          {
+        } else {
+          // training: the mask words and stash bookkeeping leave no registers for a second TMEM buffer (measured: the
+          // double-buffered variant spilled and ran 15 % slower); only the bias is prefetched a chunk ahead
+#pragma unroll 1
+          for (int c = 0; c < 8; c += 2) {
+            uint32_t v[32];
+            uint32_t m0, m1;
             const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-            m1 = dens_stage ? hidden_chunk<true>(v, bb, wb, relu, base, 4, row, dens)
-                            : hidden_chunk<false>(v, bb, wb, relu, base, 4, row, dens);
+            tmem_ld32(t_acc + 32 * c, v);
+            load8(bb, bias + 32 * (c + 1));
+            tmem_ld_wait32(v);
+            if (dens_stage) {
+              m0 = hidden_chunk<true>(v, ba, wsv, relu, base, 0, row, dens);
+              load8(wsv, p.params + L::kWS + 32 * (c + 1));
+            } else {
+              m0 = hidden_chunk<false>(v, ba, wsv, relu, base, 0, row, dens);
+            }
+            tmem_ld32(t_acc + 32 * (c + 1), v);
+            if (c + 2 < 8) load8(ba, bias + 32 * (c + 2));
+            tmem_ld_wait32(v);
+            if (dens_stage) {
+              m1 = hidden_chunk<true>(v, bb, wsv, relu, base, 4, row, dens);
+              if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
+            } else {
+              m1 = hidden_chunk<false>(v, bb, wsv, relu, base, 4, row, dens);
+            }
+            if (mask_dst != nullptr) mask_dst[c >> 1] = make_uint2(m0, m1);
           }
-          if (mask_dst != nullptr) mask_dst[c >> 1] = make_uint2(m0, m1);
         }
         if (dens_stage) {
           float raw = dens + __ldg(p.params + L::kBS);
