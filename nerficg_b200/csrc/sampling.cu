@@ -13,110 +13,174 @@ __device__ __forceinline__ float linspace_at(int k, int n, float start, float en
   return (k < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)k)) : __fsub_rn(end, __fmul_rn(step, (float)(n - k - 1)));
 }
 
+__device__ __forceinline__ float stratified_at(int k, int n, float near_plane, float far_plane, float step, bool randomize, float uk) {
+  const float t = n > 1 ? linspace_at(k, n, near_plane, far_plane, step) : near_plane;
+  if (!randomize) return t;
+  float lo = t, hi = t;
+  if (k > 0) lo = __fmul_rn(0.5f, __fadd_rn(t, linspace_at(k - 1, n, near_plane, far_plane, step)));
+  if (k < n - 1) hi = __fmul_rn(0.5f, __fadd_rn(linspace_at(k + 1, n, near_plane, far_plane, step), t));
+  return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uk));
+}
+
+// kVec = 4: n_samples % 4 == 0, one float4 of noise in and one float4 of depths out per thread and iteration
+template <int kVec>
 __global__ void __launch_bounds__(256) stratified_kernel(float* __restrict__ z, const float* __restrict__ u, int64_t total,
                                                          int n_samples, float near_plane, float far_plane) {
   const float step = n_samples > 1 ? (far_plane - near_plane) / (float)(n_samples - 1) : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % n_samples);
-    const float t = n_samples > 1 ? linspace_at(k, n_samples, near_plane, far_plane, step) : near_plane;
-    if (u == nullptr) {
-      z[i] = t;
-      continue;
+  const int64_t n_items = total / kVec;
+  const uint32_t per_ray = (uint32_t)(n_samples / kVec);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k0 = (int)((uint64_t)i % per_ray) * kVec;
+    if (kVec == 4) {
+      float4 uv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u != nullptr) uv = __ldg(reinterpret_cast<const float4*>(u) + i);
+      float4 o;
+      o.x = stratified_at(k0 + 0, n_samples, near_plane, far_plane, step, u != nullptr, uv.x);
+      o.y = stratified_at(k0 + 1, n_samples, near_plane, far_plane, step, u != nullptr, uv.y);
+      o.z = stratified_at(k0 + 2, n_samples, near_plane, far_plane, step, u != nullptr, uv.z);
+      o.w = stratified_at(k0 + 3, n_samples, near_plane, far_plane, step, u != nullptr, uv.w);
+      reinterpret_cast<float4*>(z)[i] = o;
+    } else {
+      z[i] = stratified_at(k0, n_samples, near_plane, far_plane, step, u != nullptr, u != nullptr ? __ldg(u + i) : 0.f);
     }
-    float lo = t, hi = t;
-    if (k > 0) lo = __fmul_rn(0.5f, __fadd_rn(t, linspace_at(k - 1, n_samples, near_plane, far_plane, step)));
-    if (k < n_samples - 1) hi = __fmul_rn(0.5f, __fadd_rn(linspace_at(k + 1, n_samples, near_plane, far_plane, step), t));
-    z[i] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), __ldg(u + i)));
   }
 }
 
 // ---- K2 -------------------------------------------------------------------------------
-constexpr int kWarpsPerBlock = 4;
+// One warp per ray.  The coarse depths arrive ascending, so instead of sorting the concatenated depths (reference
+// Renderer.py:70) the warp sorts only the Nf fine depths (bitonic network in shared memory) and merges the two
+// ascending lists by rank: position(coarse i) = i + #{fine < z_c[i]}, position(fine j) = j + #{coarse <= z_f[j]}
+// (two binary searches).  The cdf itself is summed by one lane in the reference's order (torch.cumsum on the
+// CPU oracle is sequential): samples that land in near-empty bins amplify cdf rounding by 1/pdf (SURVEY hard
+// part 7), so a parallel scan would break the 1e-5 parity of exactly those samples.
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float invert_cdf(const float* __restrict__ cdf, const float* __restrict__ edges, int nb, float uj) {
+  // first index with cdf > u  (searchsorted right=True); cdf[0] = 0 <= u
+  int a = 0, b = nb;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if (cdf[mid] <= uj) a = mid + 1; else b = mid;
+  }
+  const int below = max(a - 1, 0), above = min(a, nb - 1);
+  const float c0 = cdf[below], c1 = cdf[above];
+  float den = __fsub_rn(c1, c0);
+  if (den < 1e-5f) den = 1.f;
+  const float t = __fdiv_rn(__fsub_rn(uj, c0), den);
+  const float e0 = edges[below], e1 = edges[above];
+  return __fadd_rn(e0, __fmul_rn(t, __fsub_rn(e1, e0)));
+}
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) importance_kernel(
     float* __restrict__ z_merged, float* __restrict__ z_fine_out, const float* __restrict__ z_coarse,
-    const float* __restrict__ w_coarse, const float* __restrict__ u, int n_rays, int nc, int nf, int s_pad) {
+    const float* __restrict__ w_coarse, const float* __restrict__ u, int n_rays, int nc, int nf, int nf_pad) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kWarpsPerBlock + warp;
   if (ray >= n_rays) return;  // whole warp exits together; only __syncwarp is used below
   const int nb = nc - 1;      // number of bin edges == number of cdf entries
-  float* cdf = sm + warp * (2 * nb + s_pad);
+  const int nv = nc - 2;      // interior weights
+  const int s = nc + nf;
+  float* cdf = sm + warp * (3 * nb + nc + nf_pad + s);
   float* edges = cdf + nb;
-  float* zall = edges + nb;
+  float* pdf = edges + nb;    // nv entries
+  float* zcs = pdf + nb;      // nc coarse depths
+  float* fine = zcs + nc;     // nf_pad: noise, sorted in place, then the fine depths
+  float* merged = fine + nf_pad;
   const float* zc = z_coarse + (int64_t)ray * nc;
   const float* wc = w_coarse + (int64_t)ray * nc;
 
-  // bin edges (midpoints) and coarse depths into the merge buffer
+  // coarse depths, bin edges (midpoints), pdf numerators
+  float part = 0.f;
   for (int j = lane; j < nc; j += 32) {
     const float zj = __ldg(zc + j);
-    zall[j] = zj;
+    zcs[j] = zj;
     if (j < nb) edges[j] = __fmul_rn(0.5f, __fadd_rn(zj, __ldg(zc + j + 1)));
+    if (j < nv) {
+      const float v = __fadd_rn(__ldg(wc + j + 1), 1e-5f);
+      pdf[j] = v;
+      part += v;
+    }
   }
-  // pdf over the nc-2 interior weights.  The normaliser is a warp reduction; the running sum is
-  // taken sequentially by one lane in the reference's order (torch.cumsum), because samples that
-  // land in near-empty bins amplify cdf rounding by 1/pdf (SURVEY hard part 7).
-  const int nv = nc - 2;
-  float part = 0.f;
-  for (int j = lane; j < nv; j += 32) part += __fadd_rn(__ldg(wc + j + 1), 1e-5f);
+  // noise (or torch.linspace(0, 1, nf), two-sided) -> shared memory, +inf padding for the sort
+  const float inv_nf1 = nf > 1 ? 1.f / (float)(nf - 1) : 0.f;
+  for (int j = lane; j < nf_pad; j += 32) {
+    float uj = __int_as_float(0x7f800000);
+    if (j < nf) {
+      if (u != nullptr) uj = __ldg(u + (int64_t)ray * nf + j);
+      else uj = (j < nf / 2) ? __fmul_rn(inv_nf1, (float)j) : __fsub_rn(1.f, __fmul_rn(inv_nf1, (float)(nf - j - 1)));
+    }
+    fine[j] = uj;
+  }
   const float total = warp_sum(part);
-  if (lane == 0) {
+  for (int j = lane; j < nv; j += 32) pdf[j] = __fdiv_rn(pdf[j], total);
+  __syncwarp();
+  if (lane == 0) {  // sequential running sum, the reference's order
     float run = 0.f;
     cdf[0] = 0.f;
-    for (int j = 0; j < nv; ++j) {
-      run = __fadd_rn(run, __fdiv_rn(__fadd_rn(__ldg(wc + j + 1), 1e-5f), total));
+    int j = 0;
+    for (; j + 4 <= nv; j += 4) {
+      const float p0 = pdf[j], p1 = pdf[j + 1], p2 = pdf[j + 2], p3 = pdf[j + 3];
+      run = __fadd_rn(run, p0);
+      cdf[j + 1] = run;
+      run = __fadd_rn(run, p1);
+      cdf[j + 2] = run;
+      run = __fadd_rn(run, p2);
+      cdf[j + 3] = run;
+      run = __fadd_rn(run, p3);
+      cdf[j + 4] = run;
+    }
+    for (; j < nv; ++j) {
+      run = __fadd_rn(run, pdf[j]);
       cdf[j + 1] = run;
     }
   }
   __syncwarp();
-
-  // invert the cdf for every fine sample
-  const float inv_nf1 = nf > 1 ? 1.f / (float)(nf - 1) : 0.f;
+  // invert the cdf for every fine sample (in the caller's noise order), then sort the DEPTHS: they are a monotone
+  // function of the noise only up to the last bit at bin boundaries, and the output must be exactly sorted
   for (int j = lane; j < nf; j += 32) {
-    float uj;
-    if (u != nullptr) {
-      uj = __ldg(u + (int64_t)ray * nf + j);
-    } else {  // torch.linspace(0, 1, nf), two-sided
-      const float st = inv_nf1;
-      uj = (j < nf / 2) ? __fmul_rn(st, (float)j) : __fsub_rn(1.f, __fmul_rn(st, (float)(nf - j - 1)));
-    }
-    // first index with cdf > u  (searchsorted right=True); cdf[0] = 0 <= u
-    int a = 0, b = nb;
-    while (a < b) {
-      const int mid = (a + b) >> 1;
-      if (cdf[mid] <= uj) a = mid + 1; else b = mid;
-    }
-    const int below = max(a - 1, 0), above = min(a, nb - 1);
-    const float c0 = cdf[below], c1 = cdf[above];
-    float den = __fsub_rn(c1, c0);
-    if (den < 1e-5f) den = 1.f;
-    const float t = __fdiv_rn(__fsub_rn(uj, c0), den);
-    const float e0 = edges[below], e1 = edges[above];
-    const float zf = __fadd_rn(e0, __fmul_rn(t, __fsub_rn(e1, e0)));
-    zall[nc + j] = zf;
+    const float zf = invert_cdf(cdf, edges, nb, fine[j]);
+    fine[j] = zf;
     if (z_fine_out != nullptr) z_fine_out[(int64_t)ray * nf + j] = zf;
   }
-  const int s = nc + nf;
-  for (int j = s + lane; j < s_pad; j += 32) zall[j] = __int_as_float(0x7f800000);  // +inf padding
   __syncwarp();
-
-  // bitonic sort of the padded buffer (ascending)
-  for (int k = 2; k <= s_pad; k <<= 1) {
+  for (int k = 2; k <= nf_pad; k <<= 1) {  // bitonic network, ascending; +inf padding stays at the end
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < (s_pad >> 1); t += 32) {
+      for (int t = lane; t < (nf_pad >> 1); t += 32) {
         const int pos = 2 * t - (t & (j - 1));
         const int partner = pos + j;
-        const float x = zall[pos], y = zall[partner];
+        const float x = fine[pos], y = fine[partner];
         const bool up = (pos & k) == 0;
         if ((x > y) == up) {
-          zall[pos] = y;
-          zall[partner] = x;
+          fine[pos] = y;
+          fine[partner] = x;
         }
       }
       __syncwarp();
     }
   }
-  for (int j = lane; j < s; j += 32) z_merged[(int64_t)ray * s + j] = zall[j];
+  // merge by rank: position(fine j) = j + #{coarse <= z_f[j]}, position(coarse i) = i + #{fine < z_c[i]}
+  for (int j = lane; j < nf; j += 32) {
+    const float zf = fine[j];
+    int a = 0, b = nc;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (zcs[mid] <= zf) a = mid + 1; else b = mid;
+    }
+    merged[j + a] = zf;
+  }
+  __syncwarp();
+  for (int i = lane; i < nc; i += 32) {
+    const float zi = zcs[i];
+    int a = 0, b = nf;  // #{fine < zi}
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (fine[mid] < zi) a = mid + 1; else b = mid;
+    }
+    merged[i + a] = zi;
+  }
+  __syncwarp();
+  for (int j = lane; j < s; j += 32) z_merged[(int64_t)ray * s + j] = merged[j];
 }
 
 }  // namespace nerf
@@ -127,9 +191,14 @@ extern "C" int nerf_sample_stratified(float* z, const float* u, int n_rays, int 
   if (n_rays <= 0) return 0;
   NERF_CHECK_ARG(z != nullptr && n_samples >= 1, "sample_stratified: bad arguments");
   const int64_t total = (int64_t)n_rays * n_samples;
-  const int64_t want = (total + 255) / 256, cap = (int64_t)kNumSMs * 16;
+  const bool vec = n_samples % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (u == nullptr || (reinterpret_cast<uintptr_t>(u) & 15) == 0);
+  const int64_t items = vec ? total / 4 : total;
+  const int64_t want = (items + 255) / 256, cap = (int64_t)kNumSMs * 8;
   const int blocks = (int)(want < cap ? want : cap);
-  stratified_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, total, n_samples, near_plane, far_plane);
+  if (vec)
+    stratified_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, total, n_samples, near_plane, far_plane);
+  else
+    stratified_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, total, n_samples, near_plane, far_plane);
   NERF_CHECK_LAUNCH("stratified_kernel");
   return 0;
 }
@@ -142,16 +211,16 @@ extern "C" int nerf_sample_importance(float* z_merged, float* z_fine, const floa
   NERF_CHECK_ARG(n_coarse >= 3 && n_coarse <= 512, "sample_importance: n_coarse must be in [3,512], got %d", n_coarse);
   NERF_CHECK_ARG(n_fine >= 1 && n_coarse + n_fine <= 2048, "sample_importance: n_coarse+n_fine must be <= 2048");
   if (n_rays == 0) return 0;
-  int s_pad = 2;
-  while (s_pad < n_coarse + n_fine) s_pad <<= 1;
-  const size_t smem = sizeof(float) * kWarpsPerBlock * (2 * (n_coarse - 1) + s_pad);
+  int nf_pad = 2;
+  while (nf_pad < n_fine) nf_pad <<= 1;
+  const size_t smem = sizeof(float) * kWarpsPerBlock * (3 * (n_coarse - 1) + n_coarse + nf_pad + n_coarse + n_fine);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(importance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NERF_CHECK_ARG(e == cudaSuccess, "sample_importance: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   const int blocks = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
   importance_kernel<<<blocks, kWarpsPerBlock * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      z_merged, z_fine, z_coarse, w_coarse, u, n_rays, n_coarse, n_fine, s_pad);
+      z_merged, z_fine, z_coarse, w_coarse, u, n_rays, n_coarse, n_fine, nf_pad);
   NERF_CHECK_LAUNCH("importance_kernel");
   return 0;
 }
