@@ -221,10 +221,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const int tg = threadIdx.x - 128 - slot * 128;
-    const uint32_t act = smem_base + slot * kSlotBytes;
-    const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    uint32_t act = smem_base + slot * kSlotBytes;
+    uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;
-    const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
+    uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
+    asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off));  // keep in registers (see mlp_fwd.cu)
     uint32_t acc_phase = 0, load_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);

@@ -299,11 +299,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
     const int wq = warp & 3;                 // TMEM lane quarter of this warp
     const int row = wq * 32 + lane;          // row of the tile owned by this thread
     const int tg = threadIdx.x - 128 - slot * 128;  // 0..127 within the warpgroup
-    const uint32_t act = smem_base + slot * kSlotBytes;
-    const uint32_t enc = act + kActBytes;
-    const uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    uint32_t act = smem_base + slot * kSlotBytes;
+    uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;  // named barrier of this warpgroup
-    const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
+    uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
+    // opaque to the optimiser: otherwise ptxas re-derives these from %cluster_ctaid / %tid inside every chunk
+    // (S2UR + 10 dependent integer ops on the critical path of the operand stores)
+    asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off));
+    const uint32_t enc = act + kActBytes;
     uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);  // both CTAs announce their operands to the leader

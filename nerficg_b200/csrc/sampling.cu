@@ -71,7 +71,7 @@ __device__ __forceinline__ float invert_cdf(const float* __restrict__ cdf, const
   return __fadd_rn(e0, __fmul_rn(t, __fsub_rn(e1, e0)));
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) importance_kernel(
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) importance_kernel_smem(
     float* __restrict__ z_merged, float* __restrict__ z_fine_out, const float* __restrict__ z_coarse,
     const float* __restrict__ w_coarse, const float* __restrict__ u, int n_rays, int nc, int nf, int nf_pad) {
   extern __shared__ float sm[];
@@ -183,6 +183,144 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) importance_kernel(
   for (int j = lane; j < s; j += 32) z_merged[(int64_t)ray * s + j] = merged[j];
 }
 
+// ---- K2, register flavour (n_fine <= 512) ------------------------------------------------------------
+// Same algorithm, but the Nf fine depths are sorted in REGISTERS (K = ceil(Nf/32) keys per lane, element
+// e = r * 32 + lane): compare-exchange distances below 32 are one SHFL + one predicated FMNMX per key, larger
+// distances are in-lane min/max pairs with compile-time direction; the whole network is straight-line code
+// (Nf = 128: ~260 instructions instead of ~1,400 for the shared-memory network).  The K cdf inversions of a lane
+// are independent (instruction-level parallelism hides the shared-memory latency of the binary searches), and the
+// sequential cdf sums of the block's 8 rays run side by side on 8 lanes of one warp instead of on lane 0 of
+// every warp.
+template <int K>
+__device__ __forceinline__ void bitonic_sort_regs(float (&x)[K], int lane) {
+  constexpr int N = 32 * K;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j >= 1; j >>= 1) {
+      if (j < 32) {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          const bool up = k < 32 ? ((lane & k) == 0) : (((r * 32) & k) == 0);
+          const float other = __shfl_xor_sync(0xffffffffu, x[r], j);
+          x[r] = (lower == up) ? fminf(x[r], other) : fmaxf(x[r], other);
+        }
+      } else {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          if ((r & jr) == 0) {
+            const int r2 = r | jr;
+            const bool up = ((r * 32) & k) == 0;
+            const float lo = fminf(x[r], x[r2]), hi = fmaxf(x[r], x[r2]);
+            x[r] = up ? lo : hi;
+            x[r2] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) importance_kernel_reg(
+    float* __restrict__ z_merged, float* __restrict__ z_fine_out, const float* __restrict__ z_coarse,
+    const float* __restrict__ w_coarse, const float* __restrict__ u, int n_rays, int nc, int nf) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kWarpsPerBlock + warp;
+  const bool active = ray < n_rays;
+  const int nb = nc - 1, nv = nc - 2, s = nc + nf;
+  const int per_warp = 3 * nb + nc + 32 * K + s;
+  float* cdf = sm + warp * per_warp;
+  float* edges = cdf + nb;
+  float* pdf = edges + nb;
+  float* zcs = pdf + nb;
+  float* fine = zcs + nc;
+  float* merged = fine + 32 * K;
+
+  if (active) {
+    const float* zc = z_coarse + (int64_t)ray * nc;
+    const float* wc = w_coarse + (int64_t)ray * nc;
+    float part = 0.f;
+    for (int j = lane; j < nc; j += 32) {
+      const float zj = __ldg(zc + j);
+      zcs[j] = zj;
+      if (j < nb) edges[j] = __fmul_rn(0.5f, __fadd_rn(zj, __ldg(zc + j + 1)));
+      if (j < nv) {
+        const float v = __fadd_rn(__ldg(wc + j + 1), 1e-5f);
+        pdf[j] = v;
+        part += v;
+      }
+    }
+    const float total = warp_sum(part);
+    for (int j = lane; j < nv; j += 32) pdf[j] = __fdiv_rn(pdf[j], total);
+  }
+  __syncthreads();
+  if (warp == 0 && lane < kWarpsPerBlock && blockIdx.x * kWarpsPerBlock + lane < n_rays) {
+    // sequential running sums (the reference's order) of the block's rays, one lane per ray
+    float* c = sm + lane * per_warp;
+    const float* pd = c + 2 * nb;
+    float run = 0.f;
+    c[0] = 0.f;
+    for (int j = 0; j < nv; ++j) {
+      run = __fadd_rn(run, pd[j]);
+      c[j + 1] = run;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+
+  float x[K];
+  const float inv_nf1 = nf > 1 ? 1.f / (float)(nf - 1) : 0.f;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int e = r * 32 + lane;
+    float uj = 0.f;
+    if (e < nf) {
+      if (u != nullptr) uj = __ldg(u + (int64_t)ray * nf + e);
+      else uj = (e < nf / 2) ? __fmul_rn(inv_nf1, (float)e) : __fsub_rn(1.f, __fmul_rn(inv_nf1, (float)(nf - e - 1)));
+    }
+    x[r] = uj;
+  }
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int e = r * 32 + lane;
+    const float zf = invert_cdf(cdf, edges, nb, x[r]);
+    if (e < nf && z_fine_out != nullptr) z_fine_out[(int64_t)ray * nf + e] = zf;
+    x[r] = e < nf ? zf : __int_as_float(0x7f800000);  // +inf padding sorts to the end
+  }
+  bitonic_sort_regs<K>(x, lane);
+#pragma unroll
+  for (int r = 0; r < K; ++r) fine[r * 32 + lane] = x[r];
+  // merge by rank: position(fine e) = e + #{coarse <= z_f[e]}, position(coarse i) = i + #{fine < z_c[i]}
+  // (measured: early-exit searches beat branch-free fixed-trip ones here -- the kernel is bound by shared-memory
+  // bank conflicts of the data-dependent probes, not by issue slots, and early exit saves probes)
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int e = r * 32 + lane;
+    int a = 0, b = nc;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (zcs[mid] <= x[r]) a = mid + 1; else b = mid;
+    }
+    if (e < nf) merged[e + a] = x[r];
+  }
+  __syncwarp();
+  for (int i = lane; i < nc; i += 32) {
+    const float zi = zcs[i];
+    int a = 0, b = nf;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (fine[mid] < zi) a = mid + 1; else b = mid;
+    }
+    merged[i + a] = zi;
+  }
+  __syncwarp();
+  for (int j = lane; j < s; j += 32) z_merged[(int64_t)ray * s + j] = merged[j];
+}
+
 }  // namespace nerf
 
 extern "C" int nerf_sample_stratified(float* z, const float* u, int n_rays, int n_samples, float near_plane, float far_plane,
@@ -211,16 +349,36 @@ extern "C" int nerf_sample_importance(float* z_merged, float* z_fine, const floa
   NERF_CHECK_ARG(n_coarse >= 3 && n_coarse <= 512, "sample_importance: n_coarse must be in [3,512], got %d", n_coarse);
   NERF_CHECK_ARG(n_fine >= 1 && n_coarse + n_fine <= 2048, "sample_importance: n_coarse+n_fine must be <= 2048");
   if (n_rays == 0) return 0;
-  int nf_pad = 2;
+  int nf_pad = 32;
   while (nf_pad < n_fine) nf_pad <<= 1;
-  const size_t smem = sizeof(float) * kWarpsPerBlock * (3 * (n_coarse - 1) + n_coarse + nf_pad + n_coarse + n_fine);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(importance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    NERF_CHECK_ARG(e == cudaSuccess, "sample_importance: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  }
   const int blocks = (n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  importance_kernel<<<blocks, kWarpsPerBlock * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      z_merged, z_fine, z_coarse, w_coarse, u, n_rays, n_coarse, n_fine, nf_pad);
+  const size_t smem = sizeof(float) * kWarpsPerBlock * (3 * (n_coarse - 1) + n_coarse + nf_pad + n_coarse + n_fine);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define NERF_LAUNCH_K2(KK)                                                                                                   \
+  do {                                                                                                                       \
+    if (smem > 48 * 1024) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(importance_kernel_reg<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      NERF_CHECK_ARG(e == cudaSuccess, "sample_importance: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                \
+    }                                                                                                                        \
+    importance_kernel_reg<KK><<<blocks, kWarpsPerBlock * 32, smem, st>>>(z_merged, z_fine, z_coarse, w_coarse, u, n_rays,   \
+                                                                          n_coarse, n_fine);                                 \
+  } while (0)
+  switch (nf_pad / 32) {
+    case 1: NERF_LAUNCH_K2(1); break;
+    case 2: NERF_LAUNCH_K2(2); break;
+    case 4: NERF_LAUNCH_K2(4); break;
+    case 8: NERF_LAUNCH_K2(8); break;
+    case 16: NERF_LAUNCH_K2(16); break;
+    default: {  // more than 512 fine samples: shared-memory network
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(importance_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NERF_CHECK_ARG(e == cudaSuccess, "sample_importance: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      }
+      importance_kernel_smem<<<blocks, kWarpsPerBlock * 32, smem, st>>>(z_merged, z_fine, z_coarse, w_coarse, u, n_rays, n_coarse,
+                                                                        n_fine, nf_pad);
+    }
+  }
+#undef NERF_LAUNCH_K2
   NERF_CHECK_LAUNCH("importance_kernel");
   return 0;
 }
