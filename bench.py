@@ -29,7 +29,12 @@ N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 
 METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 # algorithmic work: MACs per MLP evaluation
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
-KERNELS_PER_STEP = 14       # pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2
+KERNELS_PER_STEP = 14       # OUR launches per step: pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2 (+ ~30 torch elementwise / Adam nodes)
+N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
+RENDER_VIEWS_PER_RANK = 2   # bounded sample of this rank's shard that is actually rendered and timed
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/r01_ncu_mlp_summary.md), keyed like the live table
+NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.942e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0046e9 + 4.181e9, 'K4a_mlp_dgrad_fine': 0.430e9 + 3.867e9}
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -211,7 +216,7 @@ def run_gpu_arm(args) -> None:
     model, renderer = trainer.model, trainer.renderer
     assert (renderer.n_samples_coarse_nerf, renderer.n_samples_nerf) == (N_COARSE, N_FINE)
     torch.manual_seed(1000 + rank)               # per-rank ray batches and sampling noise
-    dataset = SyntheticLegoDataset(WIDTH, HEIGHT, N_TRAIN_VIEWS, 2, seed=rank, device=dev)
+    dataset = SyntheticLegoDataset(WIDTH, HEIGHT, N_TRAIN_VIEWS, RENDER_VIEWS_PER_RANK, seed=rank, device=dev)
     dataset.precompute_rays(['train'])
     pool = dataset.ray_collection['train'].all_rays
     camera = dataset.default_camera
@@ -274,25 +279,31 @@ def run_gpu_arm(args) -> None:
     value = N_RAYS * world * args.steps / (elapsed_ms * 1e-3)
     e2e_value = N_RAYS * world * args.steps / (e2e_ms * 1e-3)
 
-    # ---- rendering throughput (second half of the metric): one 800x800 test view per rank, ray-sharded, no comms ----
-    view = dataset.test()[rank % len(dataset.test())]
+    # ---- rendering throughput (second half of the metric; config C): the 200 test views are sharded across ranks by
+    # view (dist.shard_range, no collective); every rank renders a bounded sample of ITS shard ----
+    from nerficg_b200 import dist
+    shard = dist.shard_range(N_TEST_VIEWS, rank, world)
+    test_views = dataset.test()
+    my_views = [test_views[i % len(test_views)] for i in list(shard)[:RENDER_VIEWS_PER_RANK]]
     dataset.train()
     with torch.no_grad():
-        rays = view.get_rays()
         renderer.RAY_BATCH_SIZE = 65536
-        renderer.render_rays(rays[:65536], view.camera)
+        ray_sets = [v.get_rays() for v in my_views]
+        renderer.render_rays(ray_sets[0][:65536], my_views[0].camera)
         sync_all()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        renderer.render_rays(rays, view.camera)
+        for v, rays in zip(my_views, ray_sets):
+            renderer.render_rays(rays, v.camera)
         r1.record()
         sync_all()
         render_ms = r0.elapsed_time(r1)
+    n_render_rays = sum(len(r) for r in ray_sets)
     if world > 1:
         t = torch.tensor([render_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         render_ms = t.item()
-    render_mrays = len(rays) * world / (render_ms * 1e-3) / 1e6
+    render_mrays = n_render_rays * world / (render_ms * 1e-3) / 1e6
 
     if rank != 0:
         _leave(world)   # the remaining work (per-kernel table, CPU baseline) is rank 0's alone and uses no collective
@@ -328,9 +339,18 @@ def run_gpu_arm(args) -> None:
     dom_name = max((k for k in table if 'achieved' in table[k]), key=lambda k: table[k]['ms'])
     dom = table[dom_name]
     roofline = {'kernel': dom_name, 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': dom['unit'],
-                'frac': dom['frac'], 'traffic': None, 'peak_source': peak_source + ('; sustained figure: the kernel is timed inside a long step' if dom['bound'] == 'tensor' else ''),
+                'frac': dom['frac'], 'traffic': NCU_TRAFFIC_BYTES.get(dom_name), 'traffic_unit': 'bytes per launch (ncu --set full, profiles/)', 'peak_source': peak_source + ('; sustained figure: the kernel is timed inside a long step' if dom['bound'] == 'tensor' else ''),
                 'ms_per_launch': dom['ms'], 'share_of_step': dom['share'],
                 'mlp_tensor_tflops_whole_step': (FLOP_FWD + FLOP_DGRAD + FLOP_WGRAD) * (evals['coarse'] + evals['fine']) / (elapsed_ms / args.steps) / 1e9}
+
+    # ---- config E: HBM-bound stages at 65,536 rays (L2 flushed before every timed launch) ----
+    sys.path.insert(0, str(ROOT / 'tools'))
+    import stress_sweep
+    stress = {'workload': 'config E: 65,536-ray batch, sampling + compositing only, L2 flush (512 MB fill) before every launch',
+              'peak_gbs': peaks['hbm_gbs'], 'rows': stress_sweep.run(65536, iters=5, device=str(dev))}
+    for row in stress['rows']:
+        for k in row['kernels'].values():
+            k['frac'] = round(k['gbs'] / peaks['hbm_gbs'], 3)
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     threads = torch.get_num_threads()
@@ -347,8 +367,10 @@ def run_gpu_arm(args) -> None:
                 'last_loss': losses[-1]},
         'gpu_launches': KERNELS_PER_STEP * args.steps, 'clocks': clocks.summary(),
         'roofline': roofline, 'kernels': table, 'cpu_baseline': cpu_baseline,
-        'render': {'metric': 'nerf_render_mrays_per_s', 'value': render_mrays, 'unit': 'Mrays/s', 'rays_per_gpu': len(rays),
-                   'ms': render_ms, 'tensor_tflops': FLOP_FWD * (N_COARSE + N_COARSE + N_FINE) * len(rays) * world / render_ms / 1e9},
+        'render': {'metric': 'nerf_render_mrays_per_s', 'value': render_mrays, 'unit': 'Mrays/s', 'rays_per_gpu': n_render_rays,
+                   'views_per_gpu_timed': len(my_views), 'views_in_shard': len(shard), 'ms': render_ms,
+                   'tensor_tflops': FLOP_FWD * (N_COARSE + N_COARSE + N_FINE) * n_render_rays * world / render_ms / 1e9},
+        'stress': stress,
     }), flush=True)
     _leave(world)
 

@@ -112,6 +112,14 @@ int nerf_mlp_backward_dgrad(const float* d_rgbsigma, const float* rgbsigma, cons
 int nerf_mlp_backward_wgrad(float* grads, const void* stash, const void* workspace, int n_rays, int n_samples,
                             float grad_scale, void* stream);
 
+/* ---- K7: Adam on a flat parameter buffer (torch.optim.Adam semantics: no weight decay, no amsgrad) ----------
+ * reference: src/Methods/NeRF/Trainer.py:32-37,61-63.  `state` = 4 device floats {step, 1-beta1^step,
+ * sqrt(1-beta2^step), unused}; nerf_adam_tick advances it once per optimiser step (graph-replay safe), then
+ * nerf_adam_update is called once per flat buffer.  `lr` is a DEVICE scalar (the schedule writes it asynchronously). */
+int nerf_adam_tick(float* state, float beta1, float beta2, void* stream);
+int nerf_adam_update(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const float* lr, const float* state,
+                     float beta1, float beta2, float eps, int64_t n, void* stream);
+
 /* ---- stall accounting (development aid, tools/kernel_timing.py) ---------------------------
  * Registers a device buffer of 32 uint64 counters (or NULL to switch it off, the default): the MLP kernels
  * then add the cycles selected threads spent waiting on each barrier (slot meaning: DESIGN.md "Stall accounting"). */

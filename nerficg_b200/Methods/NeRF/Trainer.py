@@ -15,6 +15,7 @@ import torch
 
 from ... import Framework, dist, ops, params
 from ...Logging import Logger
+from ...Optim.FlatAdam import FlatAdam
 from ...Optim.lr_utils import LRDecayPolicy
 from ...Optim.Samplers import DatasetSampler, RandomImageSampler, RayPoolSampler
 from ..Base.Trainer import BaseTrainer
@@ -33,15 +34,19 @@ from .Renderer import default_grad_scale
     LAMBDA_COLOR_LOSS=1.0,
     LAMBDA_ALPHA_LOSS=0.0,
     FUSED_STEP=True,
+    FLAT_ADAM=True,
 )
 class NeRFTrainer(BaseTrainer):
     def __init__(self, **kwargs) -> None:
         super().__init__(**kwargs)
         device = next(self.model.parameters()).device
         # lr lives in a device tensor so that a captured optimiser step follows the schedule
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=torch.tensor(1.0, device=device),
-                                          fused=True, capturable=True) if device.type == 'cuda' else \
-            torch.optim.Adam(self.model.parameters(), lr=1.0)
+        if device.type == 'cuda' and self.FLAT_ADAM:
+            self.optimizer = FlatAdam(self.model.blocks(), lr=1.0)          # K7: one launch per flat block buffer
+        elif device.type == 'cuda':
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=torch.tensor(1.0, device=device), fused=True, capturable=True)
+        else:
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=1.0)
         self.lr_scheduler = _LambdaLR(
             self.optimizer, lr_lambda=LRDecayPolicy(lr_init=self.LR_INIT, lr_final=self.LR_FINAL, max_steps=self.NUM_ITERATIONS),
             last_epoch=self.model.num_iterations_trained - 1)
@@ -150,6 +155,8 @@ class _FusedStep:
         self.packed = [torch.empty(ops.mlp_packed_bytes(), dtype=torch.uint8, device=dev) for _ in self.blocks]
         # persistent flat gradient buffers; parameter .grad fields are views into them
         self.grads = [torch.zeros_like(b.flat_params) for b in self.blocks]
+        if isinstance(trainer.optimizer, FlatAdam):
+            trainer.optimizer.bind_flat_grads(self.grads)
         self.scale = default_grad_scale(n_rays)
         self.world = dist.world_size()
         self.graph = None
