@@ -131,6 +131,9 @@ int nerf_debug_set_timing(void* device_buffer);
 int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream);
 /* CTA-pair flavour (cta_group::2, one 2-CTA cluster): D[256][n] = A[256][k] * B[n][k]^T, K-major fp16. */
 int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream);
+/* TMEM read-bandwidth probe (development aid): n_warps warps of one CTA issue `iters` accumulator loads each
+ * (mode 0: 32x32b.x32, 1: two x32 in flight, 2: x16); out[0] = cycles, out[1] = bytes read from TMEM. */
+int nerf_selftest_tmem_read(unsigned long long* out, int n_warps, int mode, int iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ _PROTOTYPES = {
     'nerf_debug_set_timing': (c_int, [c_void_p]),
     'nerf_selftest_umma': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_umma2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'nerf_selftest_tmem_read': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

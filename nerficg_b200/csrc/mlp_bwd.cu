@@ -18,7 +18,8 @@ namespace nerf {
 using namespace tc;
 
 namespace bwd {
-constexpr int kThreads = 384;
+constexpr int kEpiThreadsPerSlot = 256;  // 8 warps per slot: 4 TMEM lane quarters x 2 column halves (mlp_fwd.cu)
+constexpr int kThreads = 128 + 2 * kEpiThreadsPerSlot;
 constexpr int kRingStages = 6;                           // 16 KB stages: this CTA's 128-column half of one W^T panel (mlp_fwd.cu)
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 constexpr uint32_t kSlotBytes = kActBytes;
@@ -26,7 +27,10 @@ constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
-constexpr int kRegsEpilogue = 232, kRegsOther = 40;
+constexpr int kRegsEpilogue = 112, kRegsOther = 32;
+// setmaxnreg moves registers inside the CTA's OWN allocation (launch: 640 threads x 96): what the 128 producer / MMA threads
+// release (96 - 32 each = 8192) must cover what the 512 epilogue threads request (112 - 96 each = 8192), or the
+// increase blocks forever
 }  // namespace bwd
 
 struct BwdParams {
@@ -41,39 +45,39 @@ struct BwdParams {
   unsigned long long* prof;  // optional stall counters, slots 10..19 (same meaning as the forward's 0..9)
 };
 
-__device__ __forceinline__ void load8(float4 (&dst)[8], const float* src) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-}
-
-// One 32-column chunk of a dgrad epilogue: t = acc (+ dsigma_raw * w_sigma), masked by the forward ReLU bits
-// (tc.cuh relu_mask_bit layout) -> fp16 pairs -> swizzled A-operand chunk of the next stage.
+// 16 columns of a dgrad epilogue: t = acc (+ dsigma_raw * w_sigma), masked by the forward ReLU bits of half2 words
+// qbase..qbase+7 of the enclosing 32-column chunk (tc.cuh relu_mask_bit layout) -> fp16 pairs -> two 16-byte chunks
+// of the swizzled A operand of the next stage at dst0 / dst1.
 template <bool kSig>
-__device__ __forceinline__ void dgrad_chunk(const uint32_t (&v)[32], uint32_t m, const float4 (&ws)[8], float dsr,
-                                            uint32_t panel_row_base, int chunk_in_panel, int row) {
-  uint32_t w[16];
+__device__ __forceinline__ void dgrad16(const uint32_t (&v)[16], uint32_t m, int qbase, const float* __restrict__ ws, float dsr,
+                                        uint32_t dst0, uint32_t dst1) {
+  uint32_t w[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float t0 = __uint_as_float(v[4 * q + 0]), t1 = __uint_as_float(v[4 * q + 1]);
     float t2 = __uint_as_float(v[4 * q + 2]), t3 = __uint_as_float(v[4 * q + 3]);
     if (kSig) {
-      t0 = fmaf(dsr, ws[q].x, t0);
-      t1 = fmaf(dsr, ws[q].y, t1);
-      t2 = fmaf(dsr, ws[q].z, t2);
-      t3 = fmaf(dsr, ws[q].w, t3);
+      const float4 wq = __ldg(reinterpret_cast<const float4*>(ws) + q);
+      t0 = fmaf(dsr, wq.x, t0);
+      t1 = fmaf(dsr, wq.y, t1);
+      t2 = fmaf(dsr, wq.z, t2);
+      t3 = fmaf(dsr, wq.w, t3);
     }
-    t0 = (m & (1u << (2 * q))) ? t0 : 0.f;
-    t1 = (m & (1u << (16 + 2 * q))) ? t1 : 0.f;
-    t2 = (m & (1u << (2 * q + 1))) ? t2 : 0.f;
-    t3 = (m & (1u << (16 + 2 * q + 1))) ? t3 : 0.f;
+    t0 = (m & (1u << (qbase + 2 * q))) ? t0 : 0.f;
+    t1 = (m & (1u << (16 + qbase + 2 * q))) ? t1 : 0.f;
+    t2 = (m & (1u << (qbase + 2 * q + 1))) ? t2 : 0.f;
+    t3 = (m & (1u << (16 + qbase + 2 * q + 1))) ? t3 : 0.f;
     w[2 * q] = pack_half2(t0, t1);
     w[2 * q + 1] = pack_half2(t2, t3);
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    st_shared_v4(panel_row_base + ((((uint32_t)(chunk_in_panel + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1],
-                 w[4 * q + 2], w[4 * q + 3]);
+  st_shared_v4(dst0, w[0], w[1], w[2], w[3]);
+  st_shared_v4(dst1, w[4], w[5], w[6], w[7]);
 }
+
+template <bool kV>
+struct BoolTag {
+  static constexpr bool value = kV;
+};
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
   using namespace bwd;
@@ -98,7 +102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       mbar_init(bar_w_peer + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_a_ready + 8 * s, 8);  // one arrival per epilogue warp of either CTA
+      mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
       mbar_init(bar_load + 8 * s, 1);
     }
@@ -217,15 +221,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     }
   } else {
     setmaxnreg_inc<kRegsEpilogue>();
-    const int slot = (warp - 4) >> 2;
-    const int wq = warp & 3;
+    const int ew = warp - 4;                 // 0..15
+    const int slot = ew >> 3;
+    const int half = (ew >> 2) & 1;          // column half of the accumulator owned by this warp
+    const int wq = warp & 3;                 // TMEM lane quarter (hardware: warp id % 4)
     const int row = wq * 32 + lane;
-    const int tg = threadIdx.x - 128 - slot * 128;
+    const int tg = threadIdx.x - 128 - slot * kEpiThreadsPerSlot;  // 0..255 within the slot
     uint32_t act = smem_base + slot * kSlotBytes;
-    uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    uint32_t t_acc = tmem_base + slot * 256 + half * 128 + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t bar_id = 1 + slot;
     uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
-    asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off));  // keep in registers (see mlp_fwd.cu)
+    uint32_t xr = (uint32_t)(row & 7) << 4;  // swizzle term of this row
+    asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off), "+r"(xr));  // keep in registers (see mlp_fwd.cu)
+    const uint32_t act_h = act + 2 * half * kPanelBytes128 + row_off;  // this row in the first of this half's two panels
     uint32_t acc_phase = 0, load_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
@@ -242,7 +250,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
 
       auto gstash_store = [&](int region, uint32_t src, uint32_t bytes) {
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, kEpiThreadsPerSlot);
         if (tg == 0 && tile_ok) {
           bulk_s2g_hint(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes,
                         l2_evict_first());
@@ -252,11 +260,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       auto gstash_drain = [&]() {
         const long long t0 = prof ? clock64() : 0;
         if (tg == 0) bulk_wait_read<0>();
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, kEpiThreadsPerSlot);
         if (prof) t_drain += clock64() - t0;
       };
       const uint8_t* mask_base = p.stash + stash_region_offset(kStashMask, n_tiles64) +
-                                 (uint64_t)tile * stash_region_tile_bytes(kStashMask) + row * 32;
+                                 (uint64_t)tile * stash_region_tile_bytes(kStashMask) + row * 32 + half * 16;
 
       // ---------------- prologue ----------------
       const long long t_tile = prof ? clock64() : 0;
@@ -283,19 +291,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       if (tile_ok) {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
         uint8_t* hd = p.gstash + grad_region_offset(kGradHead, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(kGradHead);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < 4; ++ch) {  // each half of the row writes its four 16-byte chunks
           uint4 v = make_uint4(0, 0, 0, 0);
-          if (ch == 0) {
+          if (ch == 0 && half == 0) {
             v.x = pack_half2(dp0, dp1);
             v.y = pack_half2(dp2, dsr);
           }
-          *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, ch)) = v;
+          *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, 4 * half + ch)) = v;
         }
       }
       mbar_wait(bar_load + 8 * slot, load_phase);
       load_phase ^= 1;
+      // dL/dg for this half's 64 of the 128 colour-layer neurons: g lives in panel 2 + half, dG goes to panel half
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c0 = 64 * half + cc;
         float dg[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -307,11 +317,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           dg[4 * q + 2] = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
           dg[4 * q + 3] = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
         }
-        const uint32_t gpanel = act + (2 + (c0 >> 6)) * kPanelBytes128;
-        const uint32_t dpanel = act + (c0 >> 6) * kPanelBytes128;
+        const uint32_t gpanel = act + (2 + half) * kPanelBytes128;
+        const uint32_t dpanel = act + half * kPanelBytes128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t off = panel_chunk_offset(row, ((c0 & 63) >> 3) + q);
+          const uint32_t off = panel_chunk_offset(row, (cc >> 3) + q);
           uint32_t g0, g1, g2, g3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(gpanel + off));
           const uint32_t gw[4] = {g0, g1, g2, g3};
@@ -328,7 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       gstash_store(kGradC0, act, 2 * kPanelBytes128);
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      __syncwarp();  // one (possibly remote) arrival per warp: per-thread remote arrivals serialise on the leader's barrier
       if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
       // pull the next tile's prologue inputs (upstream gradients, outputs, G image) into L2 while this tile's chain runs:
@@ -337,13 +347,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         const int next = group_of(it + 1, slot) * 2 + (int)rank;
         if (next < p.n_tiles) {
           const int64_t en = (int64_t)next * kTile + row;
-          if (en < p.n_evals) {
+          if (half == 0 && en < p.n_evals) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_rgbsigma + en));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rgbsigma + en));
           }
-          const uint8_t* gn = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashG) + tg * 256;
+          const uint8_t* gn = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashG) + tg * 128;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + 128));
         }
       }
 
@@ -352,49 +361,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       for (int st = 0; st < kBwdStages; ++st) {
         // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
         const int mask_layer = 8 - st;  // valid for st >= 1
-        uint4 mk0 = make_uint4(~0u, ~0u, ~0u, ~0u), mk1 = mk0;
-        if (st >= 1 && tile_ok) {  // ReLU masks of the whole row (8 words), in flight while the MMAs still run
-          const uint4* mp = reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32));
-          mk0 = __ldg(mp);
-          mk1 = __ldg(mp + 1);
-        }
-        const bool sig_stage = st == 1;  // dL/dh7 also receives dsigma_raw * w_sigma
-        float4 wsv[8];
-        if (sig_stage) load8(wsv, p.params + L::kWS);
+        uint4 mk4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (st >= 1 && tile_ok)  // ReLU masks of this half of the row (4 words), in flight while the MMAs still run
+          mk4 = __ldg(reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32)));
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         gstash_drain();                 // previous image store still reads act
-        const uint32_t mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
-        uint32_t va[32], vb[32];
-        tmem_ld32(t_acc, va);
+        const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
+        // software pipeline over eight 16-column sub-chunks: the TMEM load of sub-chunk s+1 is in flight while s is processed
+        auto run = [&](auto sig_tag) {
+          constexpr bool kSig = decltype(sig_tag)::value;  // dL/dh7 also receives dsigma_raw * w_sigma
+          const float* wsp = p.params + L::kWS + 128 * half;
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_acc, va);
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-          tmem_ld_wait32(va);
-          tmem_ld32(t_acc + 32 * (c + 1), vb);
-          if (sig_stage) {
-            dgrad_chunk<true>(va, mk[c], wsv, dsr, base, 0, row);
-            load8(wsv, p.params + L::kWS + 32 * (c + 1));
-          } else {
-            dgrad_chunk<false>(va, mk[c], wsv, dsr, base, 0, row);
+          for (int s = 0; s < 8; s += 2) {
+            const uint32_t pbase = act_h + (uint32_t)(s >> 2) * kPanelBytes128;
+            const uint32_t c0 = (uint32_t)(s & 3) * 32u;  // byte offset of sub-chunk s in the (unswizzled) panel row
+            tmem_ld_wait16(va);
+            tmem_ld16(t_acc + 16 * (s + 1), vb);
+            dgrad16<kSig>(va, mk[s >> 1], 0, wsp + 16 * s, dsr, pbase + (c0 ^ xr), pbase + ((c0 + 16u) ^ xr));
+            tmem_ld_wait16(vb);
+            if (s + 2 < 8) tmem_ld16(t_acc + 16 * (s + 2), va);
+            dgrad16<kSig>(vb, mk[s >> 1], 8, wsp + 16 * (s + 1), dsr, pbase + ((c0 + 32u) ^ xr), pbase + ((c0 + 48u) ^ xr));
           }
-          tmem_ld_wait32(vb);
-          if (c + 2 < 8) tmem_ld32(t_acc + 32 * (c + 2), va);
-          if (sig_stage) {
-            dgrad_chunk<true>(vb, mk[c + 1], wsv, dsr, base, 4, row);
-            if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
-          } else {
-            dgrad_chunk<false>(vb, mk[c + 1], wsv, dsr, base, 4, row);
-          }
-        }
+        };
+        if (st == 1) run(BoolTag<true>{}); else run(BoolTag<false>{});
         gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
         if (st < kBwdStages - 1) {
           fence_proxy_async_smem();
           tc_fence_before();
-          __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
-      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+          __syncwarp();  // one (possibly remote) arrival per warp
+          if (lane == 0) mbar_arrive_cluster(a_ready_leader);
         } else {
           tc_fence_before();  // accumulator drained; released by the next tile's prologue arrive
         }

@@ -13,9 +13,13 @@
 //               peer CTA: relay -- forwards "my half of ring stage s has landed" to the leader's barrier.
 //               accumulators live in TMEM (2 slots x 256 fp32 columns = all 512 columns, in each CTA)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue of slot 0 \  tcgen05.ld accumulator -> +bias, ReLU -> fp16 -> swizzled
-//   warps 8-11  epilogue of slot 1 /  A-operand panels of the next stage (in place); the two slots
-//               ping-pong so one slot's epilogue overlaps the other slot's MMAs.
+//   warps 4-11  epilogue of slot 0 \  tcgen05.ld accumulator -> +bias, ReLU -> fp16 -> swizzled
+//   warps 12-19 epilogue of slot 1 /  A-operand panels of the next stage (in place); the two slots
+//               ping-pong so one slot's epilogue overlaps the other slot's MMAs.  Each slot has EIGHT warps:
+//               warp w owns TMEM lane quarter w % 4 (hardware rule) and column half (w / 4) % 2, so two warps
+//               per scheduler work on one accumulator.  Measured with four warps per slot: the serial loop
+//               MMA (2 K cycles) -> epilogue (4 K cycles, one latency-bound warp per scheduler) -> MMA left the
+//               tensor pipe idle half of the time.
 // The density head (256->1) and the RGB head (128->3, sigmoid) are evaluated on CUDA cores inside
 // the epilogues of stages 7 and 9, so the kernel emits packed (r,g,b,sigma) per sample.
 // Training additionally stashes every operand image the backward needs (bulk stores from shared
@@ -40,7 +44,8 @@ namespace nerf {
 using namespace tc;
 
 namespace fwd {
-constexpr int kThreads = 384;
+constexpr int kEpiThreadsPerSlot = 256;  // 8 warps: 4 TMEM lane quarters x 2 column halves
+constexpr int kThreads = 128 + 2 * kEpiThreadsPerSlot;
 // weight ring: 16 KB stages = one K panel (64 inputs) x this CTA's 128 output neurons (64 for the colour layer)
 constexpr int kRingStages = 4;
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
@@ -50,7 +55,10 @@ constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;  // + barriers + alignment slack
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
-constexpr int kRegsEpilogue = 232, kRegsOther = 40;  // 256 * 232 + 128 * 40 = 64512 <= 65536
+constexpr int kRegsEpilogue = 112, kRegsOther = 32;
+// setmaxnreg moves registers inside the CTA's OWN allocation (launch: 640 threads x 96): what the 128 producer / MMA threads
+// release (96 - 32 each = 8192) must cover what the 512 epilogue threads request (112 - 96 each = 8192), or the
+// increase blocks forever
 }  // namespace fwd
 
 struct FwdParams {
@@ -92,51 +100,66 @@ __device__ __forceinline__ void encode_axis(float v, int n_freq, float* cs_out /
   }
 }
 
-__device__ __forceinline__ void write_row_panel(uint32_t panel_smem, int row, const float* vals /*[64]*/) {
+// chunks [4 * half, 4 * half + 4) of one panel row: 32 values -> 32 halves (each column half of a row has its own thread)
+__device__ __forceinline__ void write_half_row(uint32_t panel_smem, int row, int half, const float* vals /*[32]*/) {
 #pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    st_shared_v4(panel_smem + panel_chunk_offset(row, ch), pack_half2(vals[8 * ch + 0], vals[8 * ch + 1]),
+  for (int ch = 0; ch < 4; ++ch) {
+    st_shared_v4(panel_smem + panel_chunk_offset(row, 4 * half + ch), pack_half2(vals[8 * ch + 0], vals[8 * ch + 1]),
                  pack_half2(vals[8 * ch + 2], vals[8 * ch + 3]), pack_half2(vals[8 * ch + 4], vals[8 * ch + 5]),
                  pack_half2(vals[8 * ch + 6], vals[8 * ch + 7]));
   }
 }
 
-__device__ __forceinline__ void load8(float4 (&dst)[8], const float* src) {
+__device__ __forceinline__ void load4(float4 (&dst)[4], const float* src) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+  for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
 }
 
-// One 32-column chunk of a hidden-stage epilogue: x = acc + bias [ReLU] -> fp16 pairs -> swizzled A-operand chunk.
-// Returns the ReLU bit mask (tc.cuh relu_mask_bit layout); accumulates the density head when kDens.
-template <bool kDens>
-__device__ __forceinline__ uint32_t hidden_chunk(const uint32_t (&v)[32], const float4 (&b)[8], const float4 (&ws)[8], bool relu,
-                                                 uint32_t panel_row_base, int chunk_in_panel, int row, float& dens) {
-  uint32_t w[16];
+// 16 columns of a hidden-stage epilogue: x = acc + bias [ReLU] -> fp16 pairs -> two 16-byte chunks of the swizzled
+// A operand at dst0 / dst1.  Returns the ReLU bits of half2 words qbase..qbase+7 of the enclosing 32-column chunk
+// (tc.cuh relu_mask_bit layout); accumulates the density head (fp32, from the 16 weights at ws) when kDens.
+template <bool kDens, bool kMask>
+__device__ __forceinline__ uint32_t hidden16(const uint32_t (&v)[16], const float4 (&b)[4], const float* __restrict__ ws, bool relu,
+                                             uint32_t dst0, uint32_t dst1, int qbase, float& dens) {
+  uint32_t w[8];
   uint32_t m = 0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float x0 = __uint_as_float(v[4 * q + 0]) + b[q].x;
     float x1 = __uint_as_float(v[4 * q + 1]) + b[q].y;
     float x2 = __uint_as_float(v[4 * q + 2]) + b[q].z;
     float x3 = __uint_as_float(v[4 * q + 3]) + b[q].w;
-    if (relu) {
+    if (kDens) {  // the density head reads the fp32 activations (stage 7, always ReLU)
       x0 = fmaxf(x0, 0.f);
       x1 = fmaxf(x1, 0.f);
       x2 = fmaxf(x2, 0.f);
       x3 = fmaxf(x3, 0.f);
+      const float4 wq = __ldg(reinterpret_cast<const float4*>(ws) + q);
+      dens = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, fmaf(x3, wq.w, dens))));
+      w[2 * q] = pack_half2(x0, x1);
+      w[2 * q + 1] = pack_half2(x2, x3);
+    } else {  // ReLU in the fp16 domain: one HMNMX2 per pair, same result as rounding the fp32 ReLU
+      w[2 * q] = pack_half2(x0, x1);
+      w[2 * q + 1] = pack_half2(x2, x3);
+      if (relu) {
+        w[2 * q] = half2_relu(w[2 * q]);
+        w[2 * q + 1] = half2_relu(w[2 * q + 1]);
+      }
     }
-    if (kDens) dens = fmaf(x0, ws[q].x, fmaf(x1, ws[q].y, fmaf(x2, ws[q].z, fmaf(x3, ws[q].w, dens))));
-    w[2 * q] = pack_half2(x0, x1);
-    w[2 * q + 1] = pack_half2(x2, x3);
-    m |= half2_gt0_mask(w[2 * q]) & (0x00010001u << (2 * q));
-    m |= half2_gt0_mask(w[2 * q + 1]) & (0x00010001u << (2 * q + 1));
+    if (kMask) {
+      m |= half2_gt0_mask(w[2 * q]) & (0x00010001u << (qbase + 2 * q));
+      m |= half2_gt0_mask(w[2 * q + 1]) & (0x00010001u << (qbase + 2 * q + 1));
+    }
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    st_shared_v4(panel_row_base + ((((uint32_t)(chunk_in_panel + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1],
-                 w[4 * q + 2], w[4 * q + 3]);
+  st_shared_v4(dst0, w[0], w[1], w[2], w[3]);
+  st_shared_v4(dst1, w[4], w[5], w[6], w[7]);
   return m;
 }
+
+template <bool kV>
+struct BoolTag {
+  static constexpr bool value = kV;
+};
 
 template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
@@ -162,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       mbar_init(bar_w_peer + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_a_ready + 8 * s, 8);  // one arrival per epilogue warp of either CTA
+      mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
     }
     fence_barrier_init();
@@ -293,20 +316,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           }
     }
   } else {
-    // =============================== epilogue warpgroups ===============================
+    // =============================== epilogue warps ===============================
     setmaxnreg_inc<kRegsEpilogue>();
-    const int slot = (warp - 4) >> 2;
-    const int wq = warp & 3;                 // TMEM lane quarter of this warp
-    const int row = wq * 32 + lane;          // row of the tile owned by this thread
-    const int tg = threadIdx.x - 128 - slot * 128;  // 0..127 within the warpgroup
+    const int ew = warp - 4;                 // 0..15
+    const int slot = ew >> 3;
+    const int half = (ew >> 2) & 1;          // column half of the accumulator owned by this warp
+    const int wq = warp & 3;                 // TMEM lane quarter of this warp (hardware: warp id % 4)
+    const int row = wq * 32 + lane;          // row of the tile; the thread of the other half has the same row
+    const int tg = threadIdx.x - 128 - slot * kEpiThreadsPerSlot;  // 0..255 within the slot
     uint32_t act = smem_base + slot * kSlotBytes;
-    uint32_t t_acc = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t bar_id = 1 + slot;  // named barrier of this warpgroup
+    uint32_t t_slot = tmem_base + slot * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t bar_id = 1 + slot;  // named barrier of this slot's eight warps
     uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
+    uint32_t xr = (uint32_t)(row & 7) << 4;  // swizzle term of this row: 16-byte chunk ch lives at ((ch << 4) ^ xr)
     // opaque to the optimiser: otherwise ptxas re-derives these from %cluster_ctaid / %tid inside every chunk
     // (S2UR + 10 dependent integer ops on the critical path of the operand stores)
-    asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off));
+    asm volatile("" : "+r"(act), "+r"(t_slot), "+r"(row_off), "+r"(xr));
     const uint32_t enc = act + kActBytes;
+    const uint32_t t_acc = t_slot + 128 * half;                            // hidden stages: columns [128 * half, +128)
+    const uint32_t act_h = act + 2 * half * kPanelBytes128 + row_off;      // this row in the first of this half's two panels
     uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);  // both CTAs announce their operands to the leader
@@ -323,11 +351,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       const bool valid = tile_ok && e < p.n_evals;
       const int ray = valid ? (int)(e / p.n_samples) : 0;
 
-      // stash helper: one thread bulk-stores an image from shared memory after the group fenced its writes
+      // stash helper: one thread bulk-stores an image from shared memory after the slot's warps fenced their writes
       auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {
         if (kTrain) {
           fence_proxy_async_smem();
-          named_bar_sync(bar_id, 128);
+          named_bar_sync(bar_id, kEpiThreadsPerSlot);
           if (tg == 0 && tile_ok) {
             bulk_s2g_hint(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes,
                           l2_evict_first());
@@ -340,195 +368,177 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         if (kTrain) {
           const long long t0 = prof ? clock64() : 0;
           if (tg == 0) bulk_wait_read<0>();
-          named_bar_sync(bar_id, 128);
+          named_bar_sync(bar_id, kEpiThreadsPerSlot);
           if (prof) t_drain += clock64() - t0;
         }
       };
 
-      // ---------------- prologue: position encoding -> enc panel ----------------
+      // ---------------- prologue: position encoding -> enc panel (each half writes its 32 of the 64 columns) ----------------
+      // columns: [x y z | enc(x) 3..22 | enc(y) 23..42 | enc(z) 43..62 | 0]; half 0 needs enc(x) and the first nine
+      // cosines of enc(y), half 1 the rest of enc(y) and enc(z): two sincos chains per thread instead of three
       float vdx = 0.f, vdy = 0.f, vdz = 0.f;
       {
-        float vals[64];
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
         if (valid) {
           const float zz = __ldg(p.z + e);
           x0 = __fadd_rn(__ldg(p.origins + 3 * ray + 0), __fmul_rn(__ldg(p.dirs + 3 * ray + 0), zz));
           x1 = __fadd_rn(__ldg(p.origins + 3 * ray + 1), __fmul_rn(__ldg(p.dirs + 3 * ray + 1), zz));
           x2 = __fadd_rn(__ldg(p.origins + 3 * ray + 2), __fmul_rn(__ldg(p.dirs + 3 * ray + 2), zz));
-          vdx = __ldg(p.viewdirs + 3 * ray + 0);
-          vdy = __ldg(p.viewdirs + 3 * ray + 1);
-          vdz = __ldg(p.viewdirs + 3 * ray + 2);
+          if (half == 0) {
+            vdx = __ldg(p.viewdirs + 3 * ray + 0);
+            vdy = __ldg(p.viewdirs + 3 * ray + 1);
+            vdz = __ldg(p.viewdirs + 3 * ray + 2);
+          }
         }
-        vals[0] = x0;
-        vals[1] = x1;
-        vals[2] = x2;
-        encode_axis(x0, 10, vals + 3);
-        encode_axis(x1, 10, vals + 23);
-        encode_axis(x2, 10, vals + 43);
-        vals[63] = 0.f;
+        float ea[20], eb[20], vals[32];
+        encode_axis(half == 0 ? x0 : x1, 10, ea);
+        encode_axis(half == 0 ? x1 : x2, 10, eb);
+        if (half == 0) {
+          vals[0] = x0;
+          vals[1] = x1;
+          vals[2] = x2;
+#pragma unroll
+          for (int k = 0; k < 20; ++k) vals[3 + k] = ea[k];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) vals[23 + k] = eb[k];
+        } else {
+          vals[0] = ea[9];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) vals[1 + k] = ea[10 + k];
+#pragma unroll
+          for (int k = 0; k < 20; ++k) vals[11 + k] = eb[k];
+          vals[31] = 0.f;
+        }
         stash_drain();  // previous tile's DIR / G stores still reading enc / act
-        write_row_panel(enc, row, vals);
+        write_half_row(enc, row, half, vals);
       }
       stash_store(kStashEnc, enc, kPanelBytes128);
       fence_proxy_async_smem();
       tc_fence_before();
-      __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
+      __syncwarp();  // one (possibly remote) arrival per warp: per-thread remote arrivals serialise on the leader's barrier
       if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
 
-      float sigma = 0.f;
+      float dens = 0.f;  // density head, partial sum over this thread's 128 columns (combined in stage 9)
       // ---------------- chain stages 0..8: hidden layers (ReLU) and the feature layer (linear) ----------------
 #pragma unroll 1
       for (int st = 0; st < 9; ++st) {
-        const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF);
+        const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF) + 128 * half;
         const bool relu = st < 8;
-        const bool dens_stage = st == 7;
-        float4 ba[8], bb[8], wsv[8];
-        load8(ba, bias);  // in flight while the MMAs of this stage still run
-        if (dens_stage) load8(wsv, p.params + L::kWS);
+        float4 ba[4], bb[4];
+        load4(ba, bias);  // in flight while the MMAs of this stage still run
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         stash_drain();  // the act image of the previous stage may still be being stored
-        float dens = 0.f;
-        uint2* mask_dst = nullptr;
-        if (kTrain && relu && tile_ok)
-          mask_dst = reinterpret_cast<uint2*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
-                                              (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32);
-        if (!kTrain) {
-          // software pipeline over the eight 32-column chunks: the TMEM load and the bias of chunk c+1 are in flight
-          // while chunk c is processed (va/vb and ba/bb alternate)
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_acc, va);
-#pragma unroll 1
-          for (int c = 0; c < 8; c += 2) {
-            const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-            tmem_ld_wait32(va);
-            tmem_ld32(t_acc + 32 * (c + 1), vb);
-            load8(bb, bias + 32 * (c + 1));
-            if (dens_stage) {
-              hidden_chunk<true>(va, ba, wsv, relu, base, 0, row, dens);
-              load8(wsv, p.params + L::kWS + 32 * (c + 1));
-            } else {
-              hidden_chunk<false>(va, ba, wsv, relu, base, 0, row, dens);
+        uint32_t mw[4] = {0u, 0u, 0u, 0u};  // ReLU bits of this thread's four 32-column chunks
+        // software pipeline over eight 16-column sub-chunks: the TMEM load and the bias of sub-chunk s+1 are in
+        // flight while sub-chunk s is processed (va/vb and ba/bb alternate)
+        auto run = [&](auto dens_tag) {
+          constexpr bool kDens = decltype(dens_tag)::value;
+          const float* wsp = p.params + L::kWS + 128 * half;
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_acc, va);
+#pragma unroll
+          for (int s = 0; s < 8; s += 2) {
+            const uint32_t pbase = act_h + (uint32_t)(s >> 2) * kPanelBytes128;
+            const uint32_t c0 = (uint32_t)(s & 3) * 32u;  // byte offset of sub-chunk s in the (unswizzled) panel row
+            tmem_ld_wait16(va);
+            tmem_ld16(t_acc + 16 * (s + 1), vb);
+            load4(bb, bias + 16 * (s + 1));
+            mw[s >> 1] |= hidden16<kDens, kTrain>(va, ba, wsp + 16 * s, relu, pbase + (c0 ^ xr), pbase + ((c0 + 16u) ^ xr), 0, dens);
+            tmem_ld_wait16(vb);
+            if (s + 2 < 8) {
+              tmem_ld16(t_acc + 16 * (s + 2), va);
+              load4(ba, bias + 16 * (s + 2));
             }
-            tmem_ld_wait32(vb);
-            if (c + 2 < 8) {
-              tmem_ld32(t_acc + 32 * (c + 2), va);
-              load8(ba, bias + 32 * (c + 2));
-            }
-            if (dens_stage) {
-              hidden_chunk<true>(vb, bb, wsv, relu, base, 4, row, dens);
-              if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
-            } else {
-              hidden_chunk<false>(vb, bb, wsv, relu, base, 4, row, dens);
-            }
+            mw[s >> 1] |= hidden16<kDens, kTrain>(vb, bb, wsp + 16 * (s + 1), relu, pbase + ((c0 + 32u) ^ xr), pbase + ((c0 + 48u) ^ xr), 8, dens);
           }
-        } else {
-          // training: the mask words and stash bookkeeping leave no registers for a second TMEM buffer (measured: the
-          // double-buffered variant spilled and ran 15 % slower); only the bias is prefetched a chunk ahead
-#pragma unroll 1
-          for (int c = 0; c < 8; c += 2) {
-            uint32_t v[32];
-            uint32_t m0, m1;
-            const uint32_t base = act + (c >> 1) * kPanelBytes128 + row_off;
-            tmem_ld32(t_acc + 32 * c, v);
-            load8(bb, bias + 32 * (c + 1));
-            tmem_ld_wait32(v);
-            if (dens_stage) {
-              m0 = hidden_chunk<true>(v, ba, wsv, relu, base, 0, row, dens);
-              load8(wsv, p.params + L::kWS + 32 * (c + 1));
-            } else {
-              m0 = hidden_chunk<false>(v, ba, wsv, relu, base, 0, row, dens);
-            }
-            tmem_ld32(t_acc + 32 * (c + 1), v);
-            if (c + 2 < 8) load8(ba, bias + 32 * (c + 2));
-            tmem_ld_wait32(v);
-            if (dens_stage) {
-              m1 = hidden_chunk<true>(v, bb, wsv, relu, base, 4, row, dens);
-              if (c + 2 < 8) load8(wsv, p.params + L::kWS + 32 * (c + 2));
-            } else {
-              m1 = hidden_chunk<false>(v, bb, wsv, relu, base, 4, row, dens);
-            }
-            if (mask_dst != nullptr) mask_dst[c >> 1] = make_uint2(m0, m1);
-          }
-        }
-        if (dens_stage) {
-          float raw = dens + __ldg(p.params + L::kBS);
-          if (p.noise != nullptr && valid) raw += __ldg(p.noise + e);
-          sigma = fmaxf(raw, 0.f);
+        };
+        if (st == 7) run(BoolTag<true>{}); else run(BoolTag<false>{});
+        if (kTrain && relu && tile_ok) {
+          uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
+                                               (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32 + half * 16);
+          *md = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         }
         if (st == 8) {
-          // direction encoding -> enc panel (the x encoding was last read by stage 5)
-          float vals[64];
-          vals[0] = vdx;
-          vals[1] = vdy;
-          vals[2] = vdz;
-          encode_axis(vdx, 4, vals + 3);
-          encode_axis(vdy, 4, vals + 11);
-          encode_axis(vdz, 4, vals + 19);
+          // direction encoding -> enc panel (the x encoding was last read by stage 5): 27 values in half 0, zeros beyond
+          float vals[32];
 #pragma unroll
-          for (int j = 27; j < 64; ++j) vals[j] = 0.f;
-          write_row_panel(enc, row, vals);
+          for (int j = 0; j < 32; ++j) vals[j] = 0.f;
+          if (half == 0) {
+            vals[0] = vdx;
+            vals[1] = vdy;
+            vals[2] = vdz;
+            encode_axis(vdx, 4, vals + 3);
+            encode_axis(vdy, 4, vals + 11);
+            encode_axis(vdz, 4, vals + 19);
+          }
+          write_half_row(enc, row, half, vals);
           stash_store(kStashDir, enc, kPanelBytes128);
         }
         stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
         fence_proxy_async_smem();
         tc_fence_before();
-        __syncwarp();  // one (possibly remote) arrival per warp: 128 per-thread remote arrivals serialise on the leader's barrier
-      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+        __syncwarp();  // one (possibly remote) arrival per warp
+        if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       }
       // ---------------- stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores ----------------
       {
-        float a0 = __ldg(p.params + L::kBC1 + 0), a1 = __ldg(p.params + L::kBC1 + 1), a2 = __ldg(p.params + L::kBC1 + 2);
-        float4 b4[8], w0[8], w1[8], w2[8];
-        load8(b4, p.params + L::kBC0);
-        load8(w0, p.params + L::kWC1);
-        load8(w1, p.params + L::kWC1 + 128);
-        load8(w2, p.params + L::kWC1 + 256);
+        const int cb = 64 * half;  // this thread's 64 of the 128 colour-layer neurons
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
-        stash_drain();  // the F image store reads act, which receives g below
+        stash_drain();  // the F image store reads act, which receives g (and the partial sums) below
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + c0, v);
-          tmem_ld_wait32(v);
-          uint32_t w[16];
+        for (int s = 0; s < 4; ++s) {
+          const int c0 = cb + 16 * s;
+          uint32_t v[16];
+          tmem_ld16(t_slot + c0, v);
+          const float4* b4 = reinterpret_cast<const float4*>(p.params + L::kBC0 + c0);
+          const float4* w0 = reinterpret_cast<const float4*>(p.params + L::kWC1 + c0);
+          const float4* w1 = reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0);
+          const float4* w2 = reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0);
+          tmem_ld_wait16(v);
+          uint32_t w[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float g0 = fmaxf(__uint_as_float(v[4 * q + 0]) + b4[q].x, 0.f);
-            const float g1 = fmaxf(__uint_as_float(v[4 * q + 1]) + b4[q].y, 0.f);
-            const float g2 = fmaxf(__uint_as_float(v[4 * q + 2]) + b4[q].z, 0.f);
-            const float g3 = fmaxf(__uint_as_float(v[4 * q + 3]) + b4[q].w, 0.f);
-            a0 = fmaf(g0, w0[q].x, fmaf(g1, w0[q].y, fmaf(g2, w0[q].z, fmaf(g3, w0[q].w, a0))));
-            a1 = fmaf(g0, w1[q].x, fmaf(g1, w1[q].y, fmaf(g2, w1[q].z, fmaf(g3, w1[q].w, a1))));
-            a2 = fmaf(g0, w2[q].x, fmaf(g1, w2[q].y, fmaf(g2, w2[q].z, fmaf(g3, w2[q].w, a2))));
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(b4 + q), u0 = __ldg(w0 + q), u1 = __ldg(w1 + q), u2 = __ldg(w2 + q);
+            const float g0 = fmaxf(__uint_as_float(v[4 * q + 0]) + bq.x, 0.f);
+            const float g1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bq.y, 0.f);
+            const float g2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bq.z, 0.f);
+            const float g3 = fmaxf(__uint_as_float(v[4 * q + 3]) + bq.w, 0.f);
+            a0 = fmaf(g0, u0.x, fmaf(g1, u0.y, fmaf(g2, u0.z, fmaf(g3, u0.w, a0))));
+            a1 = fmaf(g0, u1.x, fmaf(g1, u1.y, fmaf(g2, u1.z, fmaf(g3, u1.w, a1))));
+            a2 = fmaf(g0, u2.x, fmaf(g1, u2.y, fmaf(g2, u2.z, fmaf(g3, u2.w, a2))));
             w[2 * q] = pack_half2(g0, g1);
             w[2 * q + 1] = pack_half2(g2, g3);
           }
-          if (c0 + 32 < 128) {  // next chunk's constants (L1-resident after the first tile)
-            load8(b4, p.params + L::kBC0 + c0 + 32);
-            load8(w0, p.params + L::kWC1 + c0 + 32);
-            load8(w1, p.params + L::kWC1 + 128 + c0 + 32);
-            load8(w2, p.params + L::kWC1 + 256 + c0 + 32);
-          }
-          if (kTrain) {
-            const uint32_t base = act + (c0 >> 6) * kPanelBytes128 + row_off;
-            const uint32_t ch0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_shared_v4(base + ((((ch0 + q) ^ (uint32_t)(row & 7)) & 7u) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          if (kTrain) {  // g image: panel `half`, 16-byte chunks 2s and 2s+1 of the row
+            const uint32_t base = act + half * kPanelBytes128 + row_off;
+            st_shared_v4(base + (((uint32_t)(2 * s) << 4) ^ xr), w[0], w[1], w[2], w[3]);
+            st_shared_v4(base + (((uint32_t)(2 * s + 1) << 4) ^ xr), w[4], w[5], w[6], w[7]);
           }
         }
-        stash_store(kStashG, act, 2 * kPanelBytes128);
-        if (valid) {
+        // the two halves of a row meet in act panel 3 (free: F has been consumed, g only fills panels 0 and 1)
+        const uint32_t xch = act + 3 * kPanelBytes128 + (uint32_t)row * 16u;
+        if (half == 1) st_shared_v4(xch, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(dens));
+        stash_store(kStashG, act, 2 * kPanelBytes128);  // (training) its barrier also orders the exchange
+        if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        if (half == 0 && valid) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(xch));
+          a0 += __uint_as_float(r0) + __ldg(p.params + L::kBC1 + 0);
+          a1 += __uint_as_float(r1) + __ldg(p.params + L::kBC1 + 1);
+          a2 += __uint_as_float(r2) + __ldg(p.params + L::kBC1 + 2);
+          float raw = dens + __uint_as_float(r3) + __ldg(p.params + L::kBS);
+          if (p.noise != nullptr) raw += __ldg(p.noise + e);
           float4 o;
           o.x = 1.f / (1.f + expf(-a0));
           o.y = 1.f / (1.f + expf(-a1));
           o.z = 1.f / (1.f + expf(-a2));
-          o.w = sigma;
+          o.w = fmaxf(raw, 0.f);
           p.rgbsigma[e] = o;
         }
         // the accumulator has been drained; the arrive that releases it is the next tile's prologue

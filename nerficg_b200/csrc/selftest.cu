@@ -169,6 +169,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   if (warp == 0) tmem_dealloc2(tmem, 256);
 }
 
+// ---- TMEM read bandwidth probe ---------------------------------------------------------------------
+// n_warps warps (warp w: lane quarter w % 4, columns 32 * (w / 4)) each issue `iters` accumulator loads back to back:
+// mode 0 = one 32x32b.x32 load per wait, 1 = two x32 loads in flight per wait, 2 = one x16 load per wait.
+// out[0] = cycles between the two block barriers, out[1] = bytes read from TMEM.  Sizes the epilogue floor of the chain
+// kernels: every stage must read its 128 x 256 fp32 accumulator (128 KB) out of TMEM.
+__global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(unsigned long long* __restrict__ out, int mode, int iters) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_base_s + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64) % 448u;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (mode == 0) {
+      uint32_t v[32];
+      tmem_ld32(t, v);
+      tmem_ld_wait32(v);
+      acc += v[0] ^ v[31];
+    } else if (mode == 1) {
+      uint32_t v[32], w[32];
+      tmem_ld32(t, v);
+      tmem_ld32(t + 32, w);
+      tmem_ld_wait32(v);
+      asm volatile("" : "+r"(w[0]), "+r"(w[31]));
+      acc += v[0] ^ w[31];
+    } else {
+      uint32_t v[16];
+      tmem_ld16(t, v);
+      tmem_ld_wait16(v);
+      acc += v[0] ^ v[15];
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out[0] = (unsigned long long)(t1 - t0);
+    const unsigned long long per = mode == 0 ? 4096ull : (mode == 1 ? 8192ull : 2048ull);
+    out[1] = per * (unsigned long long)iters * (blockDim.x >> 5);
+  }
+  if (acc == 0x12345678u) out[2] = acc;  // keep the loads alive
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace nerf
 
 extern "C" int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream) {
@@ -193,5 +245,14 @@ extern "C" int nerf_selftest_umma(float* d_out, const float* a, const float* b, 
   NERF_CHECK_ARG(e == cudaSuccess, "selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k, mode);
   NERF_CHECK_LAUNCH("selftest_kernel");
+  return 0;
+}
+
+extern "C" int nerf_selftest_tmem_read(unsigned long long* out, int n_warps, int mode, int iters, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(out != nullptr && n_warps >= 1 && n_warps <= 16 && mode >= 0 && mode <= 2 && iters >= 1,
+                 "selftest_tmem_read: bad arguments");
+  tmem_read_probe_kernel<<<1, 32 * n_warps, 0, static_cast<cudaStream_t>(stream)>>>(out, mode, iters);
+  NERF_CHECK_LAUNCH("tmem_read_probe_kernel");
   return 0;
 }

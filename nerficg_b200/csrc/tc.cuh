@@ -143,6 +143,24 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns (the split epilogues double-buffer at this granularity)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // register reallocation between warp roles (whole warpgroups): producer / MMA warps give registers to the epilogues
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
@@ -260,6 +278,11 @@ __device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
 __device__ __forceinline__ uint32_t half2_gt0_mask(uint32_t w) {
   const __half2 z = __floats2half2_rn(0.f, 0.f);
   return __hgt2_mask(*reinterpret_cast<__half2*>(&w), z);
+}
+// max(x, 0) on both halves (one HMNMX2): ReLU after the fp16 rounding equals the rounding of the fp32 ReLU
+__device__ __forceinline__ uint32_t half2_relu(uint32_t w) {
+  const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&w), __floats2half2_rn(0.f, 0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 // ReLU mask bit layout used by the forward stash and the dgrad chain: within a 32-column chunk, column j is bit
 // (j >> 1) + 16 * (j & 1), i.e. the packed half2 word q = j >> 1 contributes bits q (low half) and 16 + q (high half).
