@@ -53,7 +53,8 @@ constexpr uint32_t kRingStageBytes = kPanelBytes128;
 constexpr uint32_t kSlotBytes = kActBytes + kPanelBytes128;  // act (4 panels) + enc (1 panel)
 constexpr uint32_t kOffRing = 2 * kSlotBytes;
 constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
-constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t kOffBias = kOffBars + 256;             // [2 slots][256 floats]: the bias vector of the stage in flight
+constexpr uint32_t kSmemBytes = kOffBias + 2 * 1024;      // the dynamic window is 1024-byte aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 constexpr int kRegsEpilogue = 112, kRegsOther = 32;
 // setmaxnreg moves registers inside the CTA's OWN allocation (launch: 640 threads x 96): what the 128 producer / MMA threads
@@ -110,25 +111,26 @@ __device__ __forceinline__ void write_half_row(uint32_t panel_smem, int row, int
   }
 }
 
-__device__ __forceinline__ void load4(float4 (&dst)[4], const float* src) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-}
-
-// 16 columns of a hidden-stage epilogue: x = acc + bias [ReLU] -> fp16 pairs -> two 16-byte chunks of the swizzled
-// A operand at dst0 / dst1.  Returns the ReLU bits of half2 words qbase..qbase+7 of the enclosing 32-column chunk
-// (tc.cuh relu_mask_bit layout); accumulates the density head (fp32, from the 16 weights at ws) when kDens.
-template <bool kDens, bool kMask>
-__device__ __forceinline__ uint32_t hidden16(const uint32_t (&v)[16], const float4 (&b)[4], const float* __restrict__ ws, bool relu,
-                                             uint32_t dst0, uint32_t dst1, int qbase, float& dens) {
-  uint32_t w[8];
+// Half (16 columns, kOff = 0 or 16) of a 32-column chunk of a hidden-stage epilogue: x = acc + bias [ReLU] -> fp16
+// pairs -> two 16-byte chunks of the swizzled A operand; c0 = byte offset of the 32-column chunk in the (unswizzled)
+// panel row.  The bias comes from the slot's shared-memory copy (one broadcast LDS.128 per four columns; from global
+// memory every ~20th load missed the 28 KB L1 and stalled the warp for an L2 round trip).  Returns the ReLU bits of
+// these 16 columns (tc.cuh relu_mask_bit layout); accumulates the density head (fp32, weights at ws) when kDens.
+template <bool kDens, bool kMask, int kOff>
+__device__ __forceinline__ uint32_t hidden16(const uint32_t (&v)[32], const float4* __restrict__ b, const float* __restrict__ ws, bool relu,
+                                             uint32_t pbase, uint32_t c0, uint32_t xr, float& dens) {
   uint32_t m = 0;
+  uint32_t w[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float x0 = __uint_as_float(v[4 * q + 0]) + b[q].x;
-    float x1 = __uint_as_float(v[4 * q + 1]) + b[q].y;
-    float x2 = __uint_as_float(v[4 * q + 2]) + b[q].z;
-    float x3 = __uint_as_float(v[4 * q + 3]) + b[q].w;
+  for (int qq = 0; qq < 4; ++qq) {
+    constexpr int kQ0 = kOff / 4;
+    const int q = kQ0 + qq;  // index of the 4-column group within the 32-column chunk
+    const float4 bq = b[q];
+    float x0 = __uint_as_float(v[4 * q + 0]) + bq.x;
+    float x1 = __uint_as_float(v[4 * q + 1]) + bq.y;
+    float x2 = __uint_as_float(v[4 * q + 2]) + bq.z;
+    float x3 = __uint_as_float(v[4 * q + 3]) + bq.w;
+    uint32_t w0, w1;
     if (kDens) {  // the density head reads the fp32 activations (stage 7, always ReLU)
       x0 = fmaxf(x0, 0.f);
       x1 = fmaxf(x1, 0.f);
@@ -136,23 +138,25 @@ __device__ __forceinline__ uint32_t hidden16(const uint32_t (&v)[16], const floa
       x3 = fmaxf(x3, 0.f);
       const float4 wq = __ldg(reinterpret_cast<const float4*>(ws) + q);
       dens = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, fmaf(x3, wq.w, dens))));
-      w[2 * q] = pack_half2(x0, x1);
-      w[2 * q + 1] = pack_half2(x2, x3);
+      w0 = pack_half2(x0, x1);
+      w1 = pack_half2(x2, x3);
     } else {  // ReLU in the fp16 domain: one HMNMX2 per pair, same result as rounding the fp32 ReLU
-      w[2 * q] = pack_half2(x0, x1);
-      w[2 * q + 1] = pack_half2(x2, x3);
+      w0 = pack_half2(x0, x1);
+      w1 = pack_half2(x2, x3);
       if (relu) {
-        w[2 * q] = half2_relu(w[2 * q]);
-        w[2 * q + 1] = half2_relu(w[2 * q + 1]);
+        w0 = half2_relu(w0);
+        w1 = half2_relu(w1);
       }
     }
     if (kMask) {
-      m |= half2_gt0_mask(w[2 * q]) & (0x00010001u << (qbase + 2 * q));
-      m |= half2_gt0_mask(w[2 * q + 1]) & (0x00010001u << (qbase + 2 * q + 1));
+      m |= half2_gt0_mask(w0) & (0x00010001u << (2 * q));
+      m |= half2_gt0_mask(w1) & (0x00010001u << (2 * q + 1));
     }
+    w[2 * qq] = w0;
+    w[2 * qq + 1] = w1;
   }
-  st_shared_v4(dst0, w[0], w[1], w[2], w[3]);
-  st_shared_v4(dst1, w[4], w[5], w[6], w[7]);
+  st_shared_v4(pbase + ((c0 + 2u * kOff) ^ xr), w[0], w[1], w[2], w[3]);
+  st_shared_v4(pbase + ((c0 + 2u * kOff + 16u) ^ xr), w[4], w[5], w[6], w[7]);
   return m;
 }
 
@@ -165,8 +169,9 @@ template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   using namespace fwd;
   using L = ParamLayout;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment and there is no slack to re-align
   const uint32_t bars = smem_base + kOffBars;
   // barrier map (8 bytes each)
   const uint32_t bar_w_full = bars;                       // [kRingStages]
@@ -174,7 +179,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
   const uint32_t bar_w_peer = bars + 16 * kRingStages;    // [kRingStages] leader only: the peer's half of the stage has landed
   const uint32_t bar_a_ready = bars + 24 * kRingStages;   // [2] leader only: operands of BOTH CTAs written + accumulators drained
   const uint32_t bar_acc_ready = bar_a_ready + 16;        // [2] accumulator complete (multicast commit)
-  const uint32_t tmem_slot = bar_acc_ready + 16;          // uint32: TMEM base address
+  const uint32_t bar_bias = bar_acc_ready + 16;           // [2] the slot's bias vector of the next stage has landed
+  const uint32_t tmem_slot = bar_bias + 16;               // uint32: TMEM base address
   const uint32_t rank = cluster_ctarank();                // 0 = leader
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,6 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
+      mbar_init(bar_bias + 8 * s, 1);
     }
     fence_barrier_init();
   }
@@ -335,10 +342,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
     const uint32_t enc = act + kActBytes;
     const uint32_t t_acc = t_slot + 128 * half;                            // hidden stages: columns [128 * half, +128)
     const uint32_t act_h = act + 2 * half * kPanelBytes128 + row_off;      // this row in the first of this half's two panels
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, bias_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);  // both CTAs announce their operands to the leader
     const bool prof = prof_on && tg == 0 && slot == 0;
+    // the bias vector of the stage in flight lives in shared memory (one buffer per slot): after the slot's warps have
+    // finished a stage (and met at a barrier) one thread bulk-copies the next stage's vector, which lands long before
+    // the next accumulator is complete
+    const float4* bias_s4 = reinterpret_cast<const float4*>(smem_raw + kOffBias + slot * 1024);
+    const uint32_t bias_u32 = smem_base + kOffBias + slot * 1024;
+    auto bias_fetch = [&](int stage) {  // one thread; stage 0..7 hidden, 8 feature, 9 colour layer 0
+      const float* src = p.params + (stage < 8 ? L::hidden_b(stage) : (stage == 8 ? L::kBF : L::kBC0));
+      const uint32_t bytes = stage == 9 ? 512u : 1024u;
+      mbar_arrive_expect_tx(bar_bias + 8 * slot, bytes);
+      bulk_g2s(bias_u32, src, bytes, bar_bias + 8 * slot);
+    };
+    if (tg == 0 && active(0, slot)) bias_fetch(0);
     long long t_accw = 0, t_drain = 0, t_pro = 0;
     const long long t_begin = prof ? clock64() : 0;
 
@@ -423,39 +442,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       // ---------------- chain stages 0..8: hidden layers (ReLU) and the feature layer (linear) ----------------
 #pragma unroll 1
       for (int st = 0; st < 9; ++st) {
-        const float* bias = p.params + (st < 8 ? L::hidden_b(st) : L::kBF) + 128 * half;
         const bool relu = st < 8;
-        float4 ba[4], bb[4];
-        load4(ba, bias);  // in flight while the MMAs of this stage still run
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
-        stash_drain();  // the act image of the previous stage may still be being stored
         uint32_t mw[4] = {0u, 0u, 0u, 0u};  // ReLU bits of this thread's four 32-column chunks
-        // software pipeline over eight 16-column sub-chunks: the TMEM load and the bias of sub-chunk s+1 are in
-        // flight while sub-chunk s is processed (va/vb and ba/bb alternate)
+        // software pipeline over the four 32-column chunks of this half (two register buffers).  The load of the next
+        // chunk is issued half way through the current one: issued right behind the shared-memory stores that last
+        // read the target registers it waits for the store queue, and ptxas then sinks it behind all the arithmetic.
+        // (Measured: with the bias in shared memory the exact position no longer matters -- 0.69 ms either way.)
         auto run = [&](auto dens_tag) {
           constexpr bool kDens = decltype(dens_tag)::value;
           const float* wsp = p.params + L::kWS + 128 * half;
-          uint32_t va[16], vb[16];
-          tmem_ld16(t_acc, va);
+          const float4* bsp = bias_s4 + 32 * half;
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_acc, va);
+          stash_drain();  // the act image of the previous stage may still be being stored
+          mbar_wait(bar_bias + 8 * slot, bias_phase);
 #pragma unroll
-          for (int s = 0; s < 8; s += 2) {
-            const uint32_t pbase = act_h + (uint32_t)(s >> 2) * kPanelBytes128;
-            const uint32_t c0 = (uint32_t)(s & 3) * 32u;  // byte offset of sub-chunk s in the (unswizzled) panel row
-            tmem_ld_wait16(va);
-            tmem_ld16(t_acc + 16 * (s + 1), vb);
-            load4(bb, bias + 16 * (s + 1));
-            mw[s >> 1] |= hidden16<kDens, kTrain>(va, ba, wsp + 16 * s, relu, pbase + (c0 ^ xr), pbase + ((c0 + 16u) ^ xr), 0, dens);
-            tmem_ld_wait16(vb);
-            if (s + 2 < 8) {
-              tmem_ld16(t_acc + 16 * (s + 2), va);
-              load4(ba, bias + 16 * (s + 2));
-            }
-            mw[s >> 1] |= hidden16<kDens, kTrain>(vb, bb, wsp + 16 * (s + 1), relu, pbase + ((c0 + 32u) ^ xr), pbase + ((c0 + 48u) ^ xr), 8, dens);
+          for (int c = 0; c < 4; c += 2) {
+            const uint32_t pbase = act_h + (uint32_t)(c >> 1) * kPanelBytes128;
+            tmem_ld_wait32(va);
+            mw[c] = hidden16<kDens, kTrain, 0>(va, bsp + 8 * c, wsp + 32 * c, relu, pbase, 0u, xr, dens);
+            tmem_ld32(t_acc + 32 * (c + 1), vb);
+            mw[c] |= hidden16<kDens, kTrain, 16>(va, bsp + 8 * c, wsp + 32 * c, relu, pbase, 0u, xr, dens);
+            tmem_ld_wait32(vb);
+            mw[c + 1] = hidden16<kDens, kTrain, 0>(vb, bsp + 8 * (c + 1), wsp + 32 * (c + 1), relu, pbase, 64u, xr, dens);
+            if (c + 2 < 4) tmem_ld32(t_acc + 32 * (c + 2), va);
+            mw[c + 1] |= hidden16<kDens, kTrain, 16>(vb, bsp + 8 * (c + 1), wsp + 32 * (c + 1), relu, pbase, 64u, xr, dens);
           }
         };
         if (st == 7) run(BoolTag<true>{}); else run(BoolTag<false>{});
+        bias_phase ^= 1;
         if (kTrain && relu && tile_ok) {
           uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
                                                (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32 + half * 16);
@@ -477,8 +495,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           write_half_row(enc, row, half, vals);
           stash_store(kStashDir, enc, kPanelBytes128);
         }
-        stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
+        stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);  // (training) fence + slot barrier + bulk store
         fence_proxy_async_smem();
+        if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);  // every warp of the slot is done with this stage's bias
+        if (tg == 0) bias_fetch(st + 1);
         tc_fence_before();
         __syncwarp();  // one (possibly remote) arrival per warp
         if (lane == 0) mbar_arrive_cluster(a_ready_leader);
@@ -491,12 +511,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         acc_phase ^= 1;
         tc_fence_after();
         stash_drain();  // the F image store reads act, which receives g (and the partial sums) below
+        mbar_wait(bar_bias + 8 * slot, bias_phase);
+        bias_phase ^= 1;
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
           const int c0 = cb + 16 * s;
           uint32_t v[16];
           tmem_ld16(t_slot + c0, v);
-          const float4* b4 = reinterpret_cast<const float4*>(p.params + L::kBC0 + c0);
+          const float4* b4 = bias_s4 + (c0 >> 2);
           const float4* w0 = reinterpret_cast<const float4*>(p.params + L::kWC1 + c0);
           const float4* w1 = reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0);
           const float4* w2 = reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0);
@@ -504,7 +526,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           uint32_t w[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(b4 + q), u0 = __ldg(w0 + q), u1 = __ldg(w1 + q), u2 = __ldg(w2 + q);
+            const float4 bq = b4[q], u0 = __ldg(w0 + q), u1 = __ldg(w1 + q), u2 = __ldg(w2 + q);
             const float g0 = fmaxf(__uint_as_float(v[4 * q + 0]) + bq.x, 0.f);
             const float g1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bq.y, 0.f);
             const float g2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bq.z, 0.f);
@@ -525,7 +547,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         const uint32_t xch = act + 3 * kPanelBytes128 + (uint32_t)row * 16u;
         if (half == 1) st_shared_v4(xch, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(dens));
         stash_store(kStashG, act, 2 * kPanelBytes128);  // (training) its barrier also orders the exchange
-        if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        if (!kTrain) {
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        }
+        if (tg == 0 && it + 1 < n_iters && active(it + 1, slot)) bias_fetch(0);  // first stage of this slot's next tile
         if (half == 0 && valid) {
           uint32_t r0, r1, r2, r3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(xch));

@@ -1,5 +1,6 @@
 """In-kernel stall accounting of the MLP kernels (nerf_debug_set_timing): where the MMA issuer, the weight producer
 and one epilogue thread of every CTA spend their cycles.  Development aid; prints averages per CTA in cycles."""
+import os
 import sys
 from pathlib import Path
 
@@ -7,6 +8,9 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from nerficg_b200 import _lib, ops, params  # noqa: E402
+
+if os.environ.get('NERF_B200_LIB'):  # development: time a variant build (csrc/build.py tag=...)
+    _lib.LIB_PATH = Path(os.environ['NERF_B200_LIB']).resolve()
 
 DEV = 'cuda:0'
 NAMES = ['mma wait A-ready', 'mma wait W-full', 'mma total', 'producer wait W-empty', 'producer total',
