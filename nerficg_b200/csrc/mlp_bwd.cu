@@ -2,7 +2,7 @@
 // warp-specialised tcgen05 kernel (mirror image of mlp_fwd.cu).
 //
 // Per 128-sample tile, starting from dL/d(r,g,b,sigma_raw) (K6 output, loss-scaled):
-//   prologue : sigmoid' and W_c1^T on CUDA cores -> dL/dg (masked by g > 0)            [128 wide]
+//   prologue : sigmoid' and W_c1^T on CUDA cores -> dL/dg (masked by the forward's g > 0 bits)  [128 wide]
 //   stage 0  : dL/df   = dG  * W_c0[:, :256]
 //   stage 1  : dL/dh7  = (dF * W_f + dsigma_raw (x) w_sigma) . [h7 > 0]
 //   stage 2+j: dL/dh_{6-j} = (dY_{7-j} * W_{7-j}[:, :256]) . [h_{6-j} > 0],  j = 0..6
@@ -90,8 +90,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
   const uint32_t bar_w_peer = bars + 16 * kRingStages;  // leader only: the peer's half of the ring stage has landed
   const uint32_t bar_a_ready = bars + 24 * kRingStages;  // leader only: both CTAs' operands written
   const uint32_t bar_acc_ready = bar_a_ready + 16;
-  const uint32_t bar_load = bar_acc_ready + 16;  // [2] G image landed in shared memory
-  const uint32_t tmem_slot = bar_load + 16;
+  const uint32_t tmem_slot = bar_acc_ready + 16;
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the cta_group::2 pair (see mlp_fwd.cu)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,7 +103,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
-      mbar_init(bar_load + 8 * s, 1);
     }
     fence_barrier_init();
   }
@@ -234,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     uint32_t xr = (uint32_t)(row & 7) << 4;  // swizzle term of this row
     asm volatile("" : "+r"(act), "+r"(t_acc), "+r"(row_off), "+r"(xr));  // keep in registers (see mlp_fwd.cu)
     const uint32_t act_h = act + 2 * half * kPanelBytes128 + row_off;  // this row in the first of this half's two panels
-    uint32_t acc_phase = 0, load_phase = 0;
+    uint32_t acc_phase = 0;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
     const bool prof = prof_on && tg == 0 && slot == 0;
@@ -268,17 +266,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
 
       // ---------------- prologue ----------------
       const long long t_tile = prof ? clock64() : 0;
-      gstash_drain();  // previous tile's D0 store still reads act
-      if (tg == 0) {   // G image (2 panels) -> act panels 2,3
-        if (tile_ok) {
-          mbar_arrive_expect_tx(bar_load + 8 * slot, 2 * kPanelBytes128);
-          bulk_g2s_hint(act + 2 * kPanelBytes128,
-                        p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashG),
-                        2 * kPanelBytes128, bar_load + 8 * slot, l2_evict_first());
-        } else {
-          mbar_arrive(bar_load + 8 * slot);  // nothing to load: whatever the panels hold is multiplied by zero gradients
-        }
-      }
+      // ReLU bits of g (this half's 64 neurons; stash mask slot 8, written by the forward's stage 9)
+      uint2 gm = make_uint2(0u, 0u);
+      if (tile_ok) gm = __ldg(reinterpret_cast<const uint2*>(mask_base + 8 * (128 * 32) - half * 8));
       float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dsr = 0.f;
       if (valid) {
         const float4 dd = __ldg(p.d_rgbsigma + e);
@@ -300,40 +290,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, 4 * half + ch)) = v;
         }
       }
-      mbar_wait(bar_load + 8 * slot, load_phase);
-      load_phase ^= 1;
-      // dL/dg for this half's 64 of the 128 colour-layer neurons: g lives in panel 2 + half, dG goes to panel half
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 32) {
-        const int c0 = 64 * half + cc;
-        float dg[32];
+      // dL/dg for this half's 64 of the 128 colour-layer neurons -> panel `half` (masked by g > 0).  Everything is computed
+      // into registers first: the previous tile's last image store (issued moments ago) still reads act, and waiting for
+      // it up front put a full store drain plus the global-load latencies on every tile's critical path.
+      uint32_t outw[2][16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = 64 * half + 32 * ci;
+        const uint32_t gbits = ci == 0 ? gm.x : gm.y;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // columns 4q..4q+3 of the chunk: half2 words 2q, 2q+1 -> bits (2q, 16+2q), (2q+1, 16+2q+1)
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + c0) + q);
           const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 128 + c0) + q);
           const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.params + L::kWC1 + 256 + c0) + q);
-          dg[4 * q + 0] = dp0 * w0.x + dp1 * w1.x + dp2 * w2.x;
-          dg[4 * q + 1] = dp0 * w0.y + dp1 * w1.y + dp2 * w2.y;
-          dg[4 * q + 2] = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
-          dg[4 * q + 3] = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
+          const float d0 = dp0 * w0.x + dp1 * w1.x + dp2 * w2.x;
+          const float d1 = dp0 * w0.y + dp1 * w1.y + dp2 * w2.y;
+          const float d2 = dp0 * w0.z + dp1 * w1.z + dp2 * w2.z;
+          const float d3 = dp0 * w0.w + dp1 * w1.w + dp2 * w2.w;
+          const bool m0 = (gbits >> (2 * q)) & 1u, m1 = (gbits >> (16 + 2 * q)) & 1u;
+          const bool m2 = (gbits >> (2 * q + 1)) & 1u, m3 = (gbits >> (16 + 2 * q + 1)) & 1u;
+          outw[ci][2 * q] = pack_half2(m0 ? d0 : 0.f, m1 ? d1 : 0.f);
+          outw[ci][2 * q + 1] = pack_half2(m2 ? d2 : 0.f, m3 ? d3 : 0.f);
         }
-        const uint32_t gpanel = act + (2 + half) * kPanelBytes128;
+      }
+      gstash_drain();  // previous tile's D0 store still reads act
+      {
         const uint32_t dpanel = act + half * kPanelBytes128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = panel_chunk_offset(row, (cc >> 3) + q);
-          uint32_t g0, g1, g2, g3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(gpanel + off));
-          const uint32_t gw[4] = {g0, g1, g2, g3};
-          uint32_t outw[4];
+        for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            // g is post-ReLU (>= 0): positive iff its fp16 bits are non-zero (and not -0)
-            const bool lo = (gw[t] & 0x7fffu) != 0, hi = (gw[t] & 0x7fff0000u) != 0;
-            outw[t] = pack_half2(lo ? dg[8 * q + 2 * t] : 0.f, hi ? dg[8 * q + 2 * t + 1] : 0.f);
-          }
-          st_shared_v4(dpanel + off, outw[0], outw[1], outw[2], outw[3]);
-        }
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(dpanel + panel_chunk_offset(row, 4 * ci + q), outw[ci][4 * q], outw[ci][4 * q + 1], outw[ci][4 * q + 2],
+                         outw[ci][4 * q + 3]);
       }
       gstash_store(kGradC0, act, 2 * kPanelBytes128);
       fence_proxy_async_smem();
@@ -351,8 +339,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_rgbsigma + en));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rgbsigma + en));
           }
-          const uint8_t* gn = p.stash + stash_region_offset(kStashG, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashG) + tg * 128;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
+          if (tg < 32) {  // the next tile's g bits (4 KB)
+            const uint8_t* gn = p.stash + stash_region_offset(kStashMask, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashMask) +
+                                8 * (128 * 32) + tg * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
+          }
         }
       }
 

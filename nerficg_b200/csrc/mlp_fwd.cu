@@ -507,6 +507,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       {
         const int cb = 64 * half;  // this thread's 64 of the 128 colour-layer neurons
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        uint32_t gm0 = 0u, gm1 = 0u;  // ReLU bits of this thread's two 32-column chunks of g
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
@@ -536,6 +537,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             a2 = fmaf(g0, u2.x, fmaf(g1, u2.y, fmaf(g2, u2.z, fmaf(g3, u2.w, a2))));
             w[2 * q] = pack_half2(g0, g1);
             w[2 * q + 1] = pack_half2(g2, g3);
+            if (kTrain) {  // ReLU bits of g for the dgrad prologue (it no longer has to fetch the 32 KB G image for its signs)
+              const uint32_t sh = (uint32_t)((s & 1) * 8 + 2 * q);
+              const uint32_t bits = (half2_gt0_mask(w[2 * q]) & (0x00010001u << sh)) | (half2_gt0_mask(w[2 * q + 1]) & (0x00010001u << (sh + 1)));
+              if (s < 2) gm0 |= bits; else gm1 |= bits;
+            }
           }
           if (kTrain) {  // g image: panel `half`, 16-byte chunks 2s and 2s+1 of the row
             const uint32_t base = act + half * kPanelBytes128 + row_off;
@@ -543,6 +549,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             st_shared_v4(base + (((uint32_t)(2 * s + 1) << 4) ^ xr), w[4], w[5], w[6], w[7]);
           }
         }
+        if (kTrain && tile_ok)
+          *reinterpret_cast<uint2*>(p.stash + stash_region_offset(kStashMask, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashMask) +
+                                    8 * (128 * 32) + row * 32 + half * 8) = make_uint2(gm0, gm1);
         // the two halves of a row meet in act panel 3 (free: F has been consumed, g only fills panels 0 and 1)
         const uint32_t xch = act + 3 * kPanelBytes128 + (uint32_t)row * 16u;
         if (half == 1) st_shared_v4(xch, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(dens));

@@ -45,10 +45,11 @@ constexpr uint32_t kBwdImageBytes = kBwdPanels * kPanelBytes256;
 constexpr uint32_t kPackedBytes = kFwdImageBytes + kBwdImageBytes;
 
 // ---- activation stash written by the training forward (per tile, region-major) -----------
-// regions: ENC (x encoding, 1 panel), H0..H7 (4 panels each), F (4), DIR (1), G (2), MASK (8 x 32 B per row)
+// regions: ENC (x encoding, 1 panel), H0..H7 (4 panels each), F (4), DIR (1), G (2),
+//          MASK (9 x 32 B per row: ReLU bits of h0..h7 (256 each) and, in slot 8, of g (128 bits, first 16 bytes))
 enum StashRegion { kStashEnc = 0, kStashH0 = 1, kStashF = 9, kStashDir = 10, kStashG = 11, kStashMask = 12, kStashRegions = 13 };
 __host__ __device__ constexpr uint32_t stash_region_tile_bytes(int r) {
-  return r == kStashEnc || r == kStashDir ? kPanelBytes128 : (r == kStashG ? 2 * kPanelBytes128 : (r == kStashMask ? 8 * 128 * 32 : kActBytes));
+  return r == kStashEnc || r == kStashDir ? kPanelBytes128 : (r == kStashG ? 2 * kPanelBytes128 : (r == kStashMask ? 9 * 128 * 32 : kActBytes));
 }
 __host__ __device__ constexpr uint64_t stash_tile_bytes_total() {
   uint64_t t = 0;

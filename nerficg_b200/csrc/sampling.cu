@@ -22,26 +22,44 @@ __device__ __forceinline__ float stratified_at(int k, int n, float near_plane, f
   return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), uk));
 }
 
-// kVec = 4: n_samples % 4 == 0, one float4 of noise in and one float4 of depths out per thread and iteration
+// kVec = 4: n_samples % 4 == 0, one float4 of noise in and one float4 of depths out per item.  Every thread owns four
+// items a grid stride apart and issues its four loads before any arithmetic (memory-level parallelism: the kernel is a
+// 5-20 us streaming pass, so bytes in flight per SM decide its bandwidth); item indices are 32-bit (host-checked).
 template <int kVec>
-__global__ void __launch_bounds__(256) stratified_kernel(float* __restrict__ z, const float* __restrict__ u, int64_t total,
+__global__ void __launch_bounds__(256) stratified_kernel(float* __restrict__ z, const float* __restrict__ u, uint32_t n_items,
                                                          int n_samples, float near_plane, float far_plane) {
   const float step = n_samples > 1 ? (far_plane - near_plane) / (float)(n_samples - 1) : 0.f;
-  const int64_t n_items = total / kVec;
   const uint32_t per_ray = (uint32_t)(n_samples / kVec);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k0 = (int)((uint64_t)i % per_ray) * kVec;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const bool randomize = u != nullptr;
+  for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < n_items; base += 4u * stride) {
     if (kVec == 4) {
-      float4 uv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (u != nullptr) uv = __ldg(reinterpret_cast<const float4*>(u) + i);
-      float4 o;
-      o.x = stratified_at(k0 + 0, n_samples, near_plane, far_plane, step, u != nullptr, uv.x);
-      o.y = stratified_at(k0 + 1, n_samples, near_plane, far_plane, step, u != nullptr, uv.y);
-      o.z = stratified_at(k0 + 2, n_samples, near_plane, far_plane, step, u != nullptr, uv.z);
-      o.w = stratified_at(k0 + 3, n_samples, near_plane, far_plane, step, u != nullptr, uv.w);
-      reinterpret_cast<float4*>(z)[i] = o;
+      float4 uv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * stride;
+        uv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (randomize && i < n_items) uv[k] = __ldcs(reinterpret_cast<const float4*>(u) + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * stride;
+        if (i >= n_items) break;
+        const int k0 = (int)(i % per_ray) * 4;
+        float4 o;
+        o.x = stratified_at(k0 + 0, n_samples, near_plane, far_plane, step, randomize, uv[k].x);
+        o.y = stratified_at(k0 + 1, n_samples, near_plane, far_plane, step, randomize, uv[k].y);
+        o.z = stratified_at(k0 + 2, n_samples, near_plane, far_plane, step, randomize, uv[k].z);
+        o.w = stratified_at(k0 + 3, n_samples, near_plane, far_plane, step, randomize, uv[k].w);
+        reinterpret_cast<float4*>(z)[i] = o;
+      }
     } else {
-      z[i] = stratified_at(k0, n_samples, near_plane, far_plane, step, u != nullptr, u != nullptr ? __ldg(u + i) : 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * stride;
+        if (i >= n_items) break;
+        z[i] = stratified_at((int)(i % per_ray), n_samples, near_plane, far_plane, step, randomize, randomize ? __ldg(u + i) : 0.f);
+      }
     }
   }
 }
@@ -329,14 +347,15 @@ extern "C" int nerf_sample_stratified(float* z, const float* u, int n_rays, int 
   if (n_rays <= 0) return 0;
   NERF_CHECK_ARG(z != nullptr && n_samples >= 1, "sample_stratified: bad arguments");
   const int64_t total = (int64_t)n_rays * n_samples;
+  NERF_CHECK_ARG(total < (int64_t(1) << 31), "sample_stratified: n_rays*n_samples must be < 2^31 per call");
   const bool vec = n_samples % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (u == nullptr || (reinterpret_cast<uintptr_t>(u) & 15) == 0);
-  const int64_t items = vec ? total / 4 : total;
-  const int64_t want = (items + 255) / 256, cap = (int64_t)kNumSMs * 8;
+  const uint32_t items = (uint32_t)(vec ? total / 4 : total);
+  const int64_t want = ((int64_t)items + 1023) / 1024, cap = (int64_t)kNumSMs * 16;  // four items per thread
   const int blocks = (int)(want < cap ? want : cap);
   if (vec)
-    stratified_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, total, n_samples, near_plane, far_plane);
+    stratified_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, items, n_samples, near_plane, far_plane);
   else
-    stratified_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, total, n_samples, near_plane, far_plane);
+    stratified_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, u, items, n_samples, near_plane, far_plane);
   NERF_CHECK_LAUNCH("stratified_kernel");
   return 0;
 }

@@ -2,7 +2,7 @@
 
 65,536-ray batch, (Nc, Nf) in {(64,64), (64,128), (64,192), (128,256), (128,384)}; inputs as SURVEY.md 8(d):
 sigma ~ Exp(1) * Bernoulli(0.5), colour ~ U[0,1], z sorted U[2,6], seed 0.  Every launch is timed alone with CUDA
-events on the launching stream after an L2 flush (a 512 MB fill), median of `iters`; the achieved figure is the
+events on the launching stream after an L2 flush (a 512 MB fill followed by a 512 MB read), median of `iters`; the achieved figure is the
 ALGORITHMIC bytes of SURVEY.md 8(d) / DESIGN.md divided by that time.
 
     python tools/stress_sweep.py [--json] [--rays 65536] [--iters 7] [--profile]   (--profile: one launch each, for ncu)
@@ -36,6 +36,7 @@ def algorithmic_bytes(n: int, nc: int, nf: int) -> dict:
 def run(n_rays: int = 65536, iters: int = 7, profile: bool = False, device: str = 'cuda:0') -> list[dict]:
     dev = torch.device(device)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(128 << 20, dtype=torch.int32, device=dev)   # 512 MB read back after the fill (see timed())
     g = torch.Generator(device=dev).manual_seed(0)
     dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g, device=dev), dim=-1) * 1.05
     bg = torch.ones(3, device=dev)
@@ -45,7 +46,11 @@ def run(n_rays: int = 65536, iters: int = 7, profile: bool = False, device: str 
     def timed(fn) -> float:
         ts = []
         for _ in range(1 if profile else iters + 2):
+            # flush L2: write 512 MB, then READ 512 MB so that the cache is left full of clean lines -- after a pure
+            # write flush the timed kernel pays for the write-back of the flush's dirty lines (measured: 5-20 us
+            # kernels lost up to half of their bandwidth to it)
             flush.fill_(1)
+            flush_rd.sum()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
