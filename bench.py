@@ -29,12 +29,12 @@ N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 
 METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 # algorithmic work: MACs per MLP evaluation
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
-KERNELS_PER_STEP = 14       # OUR launches per step: pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2 (+ ~30 torch elementwise / Adam nodes)
+KERNELS_PER_STEP = 17       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~27 torch elementwise / gather nodes)
 N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
 RENDER_VIEWS_PER_RANK = 2   # bounded sample of this rank's shard that is actually rendered and timed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_mlp_summary.md), keyed like the live table
-NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.942e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0046e9 + 4.181e9, 'K4a_mlp_dgrad_fine': 0.430e9 + 3.867e9}
+NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -346,7 +346,7 @@ def run_gpu_arm(args) -> None:
     # ---- config E: HBM-bound stages at 65,536 rays (L2 flushed before every timed launch) ----
     sys.path.insert(0, str(ROOT / 'tools'))
     import stress_sweep
-    stress = {'workload': 'config E: 65,536-ray batch, sampling + compositing only, L2 flush (512 MB fill) before every launch',
+    stress = {'workload': 'config E: 65,536-ray batch, sampling + compositing only, L2 flush (512 MB fill + 512 MB read) before every launch',
               'peak_gbs': peaks['hbm_gbs'], 'rows': stress_sweep.run(65536, iters=5, device=str(dev))}
     for row in stress['rows']:
         for k in row['kernels'].values():
