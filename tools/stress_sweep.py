@@ -11,13 +11,17 @@ from __future__ import annotations
 
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from nerficg_b200 import ops  # noqa: E402
+from nerficg_b200 import _lib, ops  # noqa: E402
+
+if os.environ.get('NERF_B200_LIB'):  # development: time a variant build (csrc/build.py tag=...)
+    _lib.LIB_PATH = Path(os.environ['NERF_B200_LIB']).resolve()
 
 SWEEP = ((64, 64), (64, 128), (64, 192), (128, 256), (128, 384))
 
