@@ -120,6 +120,16 @@ int nerf_adam_tick(float* state, float beta1, float beta2, void* stream);
 int nerf_adam_update(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const float* lr, const float* state,
                      float beta1, float beta2, float eps, int64_t n, void* stream);
 
+/* K8 -- NeRFLoss.forward and its gradient in one launch (reference src/Methods/NeRF/Loss.py:26-43,
+ * src/Datasets/utils.py:185-189, src/Optim/Losses/utils.py:54-57):
+ *   gt = clamp(lerp(background, rgb_gt, alpha_gt), 0, 1)            (alpha_gt NULL = 1, background NULL = 0)
+ *   *loss = lambda_color * [mse(rgb, gt) + mse(rgb_coarse, gt)] + lambda_alpha * [mse(alpha, alpha_gt) + mse(alpha_coarse, alpha_gt)]
+ *   g_rgb[n][3] = dloss/drgb, g_rgb_coarse, g_alpha[n], g_alpha_coarse likewise (the coarse / alpha pointers may be NULL;
+ *   the alpha gradients are only written when lambda_alpha > 0).  One block: the reduction order is fixed. */
+int nerf_loss_mse(float* loss, float* g_rgb, float* g_rgb_coarse, float* g_alpha, float* g_alpha_coarse, const float* rgb,
+                  const float* rgb_coarse, const float* alpha, const float* alpha_coarse, const float* rgb_gt,
+                  const float* alpha_gt, const float* background, int n_rays, float lambda_color, float lambda_alpha, void* stream);
+
 /* ---- stall accounting (development aid, tools/kernel_timing.py) ---------------------------
  * Registers a device buffer of 32 uint64 counters (or NULL to switch it off, the default): the MLP kernels
  * then add the cycles selected threads spent waiting on each barrier (slot meaning: DESIGN.md "Stall accounting"). */

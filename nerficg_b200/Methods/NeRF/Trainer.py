@@ -189,34 +189,20 @@ class _FusedStep:
         n_f = std * torch.randn((z.numel(), 1), dtype=torch.float32, device=dev) if std > 0 else None
         rs_f = ops.mlp_forward(self.packed[fine], flats[fine], self.origin, self.direction, self.view_direction, z, n_f, self.stash[fine])
         rgb, _, alpha, _ = ops.composite_forward(z, rs_f, self.direction, self.bg)
-        # NeRFLoss (reference Loss.py:26-43) and its gradient, written out
-        gt = torch.lerp(self.bg.expand_as(self.rgb_gt), self.rgb_gt, self.alpha_gt).clamp(0, 1)
+        # K8: NeRFLoss (reference Loss.py:26-43) and its gradient for both passes in one launch
         lc, la = float(t.LAMBDA_COLOR_LOSS), float(t.LAMBDA_ALPHA_LOSS)
-        diff = rgb - gt
-        loss = lc * diff.square().mean()
-        g_rgb = diff * (2.0 * lc / diff.numel())
-        g_alpha = None
-        if la > 0:
-            da = alpha - self.alpha_gt
-            loss = loss + la * da.square().mean()
-            g_alpha = (da * (2.0 * la / da.numel())).reshape(-1)
+        coarse = self.nc > 0
+        _, g_rgb, g_rgb_c, g_alpha, g_alpha_c = ops.loss_mse(
+            rgb, rgb_c if coarse else None, alpha.reshape(-1), alpha_c.reshape(-1) if coarse else None, self.rgb_gt,
+            self.alpha_gt.reshape(-1), self.bg, lc, la, loss_out=self.loss_out)
         for g in self.grads:
             g.zero_()
         d_rs = ops.composite_backward(z, rs_f, self.direction, self.bg, g_rgb, None, g_alpha, True, self.scale)
         ops.mlp_backward(self.grads[fine], d_rs, rs_f, self.stash[fine], self.ws, self.packed[fine], flats[fine], n, z.shape[1], self.scale)
-        if self.nc > 0:
-            diff_c = rgb_c - gt
-            loss = loss + lc * diff_c.square().mean()
-            g_rgb_c = diff_c * (2.0 * lc / diff_c.numel())
-            g_alpha_c = None
-            if la > 0:
-                dac = alpha_c - self.alpha_gt
-                loss = loss + la * dac.square().mean()
-                g_alpha_c = (dac * (2.0 * la / dac.numel())).reshape(-1)
+        if coarse:
             d_rs_c = ops.composite_backward(z_c, rs_c, self.direction, self.bg, g_rgb_c, None, g_alpha_c, True, self.scale)
             ops.mlp_backward(self.grads[0], d_rs_c, rs_c, self.stash[0], self.ws, self.packed[0], flats[0], n, self.nc, self.scale)
         dist.allreduce_mean_(self.grads)
-        self.loss_out.copy_(loss)
         t.optimizer.step()
 
     @torch.no_grad()

@@ -81,6 +81,29 @@ def composite_backward(z, rgbsigma, dirs, background, g_rgb, g_depth=None, g_alp
     return out
 
 
+
+def loss_mse(rgb: torch.Tensor, rgb_coarse: torch.Tensor | None, alpha: torch.Tensor | None, alpha_coarse: torch.Tensor | None,
+             rgb_gt: torch.Tensor, alpha_gt: torch.Tensor | None, background: torch.Tensor | None, lambda_color: float,
+             lambda_alpha: float, loss_out: torch.Tensor | None = None):
+    """K8 -- NeRFLoss.forward + gradient (reference src/Methods/NeRF/Loss.py:26-43).  Returns
+    (loss scalar tensor, g_rgb, g_rgb_coarse | None, g_alpha | None, g_alpha_coarse | None)."""
+    rgb, rgb_coarse, alpha, alpha_coarse = _f32c(rgb), _f32c(rgb_coarse), _f32c(alpha), _f32c(alpha_coarse)
+    rgb_gt, alpha_gt, background = _f32c(rgb_gt), _f32c(alpha_gt), _f32c(background)
+    require_device(rgb)
+    n = rgb.shape[0]
+    if tuple(rgb.shape) != (n, 3) or tuple(rgb_gt.shape) != (n, 3):
+        raise ValueError('rgb and rgb_gt must have shape (n, 3)')
+    loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=rgb.device)
+    g_rgb = torch.empty_like(rgb)
+    g_rgb_c = torch.empty_like(rgb_coarse) if rgb_coarse is not None else None
+    with_alpha = lambda_alpha > 0 and alpha is not None
+    g_alpha = torch.empty(n, dtype=torch.float32, device=rgb.device) if with_alpha else None
+    g_alpha_c = torch.empty(n, dtype=torch.float32, device=rgb.device) if with_alpha and alpha_coarse is not None else None
+    check(load().nerf_loss_mse(ptr(loss), ptr(g_rgb), ptr(g_rgb_c), ptr(g_alpha), ptr(g_alpha_c), ptr(rgb), ptr(rgb_coarse),
+                               ptr(alpha if with_alpha else None), ptr(alpha_coarse if with_alpha else None), ptr(rgb_gt), ptr(alpha_gt),
+                               ptr(background), n, float(lambda_color), float(lambda_alpha), stream_ptr()), 'nerf_loss_mse')
+    return loss, g_rgb, g_rgb_c, g_alpha, g_alpha_c
+
 def mlp_packed_bytes() -> int:
     return int(load().nerf_mlp_packed_bytes())
 

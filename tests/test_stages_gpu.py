@@ -164,3 +164,30 @@ def test_composite_no_background_and_empty(ops):
     assert (rgb.cpu() - rgb_o).abs().max() <= 1e-5
     e = ops.composite_forward(z[:0].to(DEV), rs[:0], d[:0].to(DEV), None)
     assert e[0].shape == (0, 3)
+
+
+@pytest.mark.parametrize('n,lam_a,coarse', [(4096, 0.0, True), (1000, 0.3, True), (77, 0.5, False), (1, 0.0, True), (70000, 0.1, True)])
+def test_loss_kernel_oracle(ops, n, lam_a, coarse):
+    """K8 against the oracle's NeRFLoss (reference Loss.py:26-43) and autograd of it."""
+    g = torch.Generator().manual_seed(n)
+    mk = lambda *shape: torch.rand(*shape, generator=g)
+    out = {'rgb': mk(n, 3).requires_grad_(True), 'alpha': mk(n, 1).requires_grad_(True)}
+    if coarse:
+        out |= {'rgb_coarse': mk(n, 3).requires_grad_(True), 'alpha_coarse': mk(n, 1).requires_grad_(True)}
+    rgb_gt, alpha_gt, bg = mk(n, 3) * 1.2 - 0.1, (mk(n, 1) * 1.4 - 0.2).clamp(0, 1), torch.tensor([1.0, 0.6, 0.2])
+    ref = O.nerf_loss(out, rgb_gt, alpha_gt, bg, lambda_color=0.7, lambda_alpha=lam_a)
+    ref.backward()
+    dev = lambda t: None if t is None else t.detach().to(DEV)
+    loss, g_rgb, g_rgb_c, g_alpha, g_alpha_c = ops.loss_mse(dev(out['rgb']), dev(out.get('rgb_coarse')), dev(out['alpha']).reshape(-1),
+                                                           dev(out['alpha_coarse']).reshape(-1) if coarse else None, dev(rgb_gt),
+                                                           dev(alpha_gt).reshape(-1), dev(bg), 0.7, lam_a)
+    assert abs(loss.item() - ref.item()) <= 1e-6 + 1e-5 * abs(ref.item())
+    assert (g_rgb.cpu() - out['rgb'].grad).abs().max() <= 1e-7 + 1e-5 * out['rgb'].grad.abs().max()
+    if coarse:
+        assert (g_rgb_c.cpu() - out['rgb_coarse'].grad).abs().max() <= 1e-7 + 1e-5 * out['rgb_coarse'].grad.abs().max()
+    if lam_a > 0:
+        assert (g_alpha.cpu() - out['alpha'].grad.reshape(-1)).abs().max() <= 1e-7 + 1e-5 * out['alpha'].grad.abs().max()
+        if coarse:
+            assert (g_alpha_c.cpu() - out['alpha_coarse'].grad.reshape(-1)).abs().max() <= 1e-7
+    else:
+        assert g_alpha is None and g_alpha_c is None
