@@ -135,6 +135,20 @@ int nerf_loss_mse(float* loss, float* g_rgb, float* g_rgb_coarse, float* g_alpha
  * then add the cycles selected threads spent waiting on each barrier (slot meaning: DESIGN.md "Stall accounting"). */
 int nerf_debug_set_timing(void* device_buffer);
 
+/* K0 -- device-side ray generation.  View.get_rays (reference src/Datasets/utils.py:1053-1074) with
+ * PerspectiveCamera.compute_local_ray_directions (src/Cameras/Perspective.py:64-94, no distortion) and View.cam_to_world
+ * (utils.py:1033-1038): origin = camera position, direction = (x, y, 1) @ R^T (NOT normalised), view_direction =
+ * normalize(direction), for the pixels `pixel_ids` (row-major ids, DEVICE int64) or, when NULL, for all width*height pixels.
+ * c2w_host: HOST pointer to a row-major 3x4 / 4x4 float64 camera-to-world matrix (row stride 4), as View stores it. */
+int nerf_generate_rays(float* origin, float* direction, float* view_direction, const int64_t* pixel_ids, int64_t n_rays,
+                       const double* c2w_host, int width, int height, double focal_x, double focal_y, double center_x,
+                       double center_y, void* stream);
+/* RayBatch.__getitem__(index tensor) (reference src/Datasets/utils.py:598-613): gathers origin / direction / view_direction /
+ * rgb ([n][3]) and alpha ([n]) of the rays `ids` (DEVICE int64) in one launch; any src/dst pair may be NULL. */
+int nerf_gather_rays(float* origin_dst, float* direction_dst, float* view_direction_dst, float* rgb_dst, float* alpha_dst,
+                     const float* origin_src, const float* direction_src, const float* view_direction_src, const float* rgb_src,
+                     const float* alpha_src, const int64_t* ids, int64_t n_rays, void* stream);
+
 /* ---- self test of the tcgen05 building blocks (used by tests/ only) --------------------
  * D[128][n] = A[128][k] * B[n][k]^T with operand images built on device; mode selects the
  * descriptor flavour (0: K-major fp16, 1: MN-major operands as in wgrad, 2: K-major bf16). */

@@ -60,7 +60,31 @@ class RayBatch:
             return self
         if isinstance(idx, int):
             idx = slice(idx, idx + 1)
+        if isinstance(idx, torch.Tensor) and idx.dtype == torch.int64 and idx.dim() == 1 and idx.is_cuda and self.origin.is_cuda:
+            return self._gather(idx)
         return self._map(lambda t: t[idx])
+
+    _GATHERED = ('origin', 'direction', 'view_direction', 'rgb', 'alpha')
+
+    def _gather(self, ids: torch.Tensor) -> 'RayBatch':
+        """Index-tensor selection through ONE `nerf_gather_rays` launch for the five fields of the training batch
+        (reference RayBatch.__getitem__, Datasets/utils.py:598-613, is one torch gather per field)."""
+        from .. import ops
+        n = ids.numel()
+        src, dst, out = {}, {}, {}
+        for k in self._FIELDS:
+            t = getattr(self, k)
+            if t is None:
+                out[k] = None
+            elif k in self._GATHERED and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 2 and \
+                    t.shape[1] == (1 if k == 'alpha' else 3):
+                src[k] = t
+                dst[k] = out[k] = torch.empty((n, t.shape[1]), dtype=torch.float32, device=t.device)
+            else:
+                out[k] = t[ids]
+        if src:
+            ops.gather_rays(dst, src, ids)
+        return RayBatch(**out, _skip_post_init=True)
 
     def to(self, dtype: torch.dtype = None, device: torch.device = None, non_blocking: bool = False) -> 'RayBatch':
         if (dtype is None or dtype == self.dtype) and (device is None or torch.device(device) == self.device):
@@ -137,14 +161,23 @@ class View:
     def rotation(self) -> torch.Tensor:
         return self.c2w[:3, :3]
 
-    def get_rays(self) -> RayBatch:
-        """Rays of every pixel (row-major) on the default CUDA device."""
+    def get_rays(self, pixel_ids: torch.Tensor | None = None) -> RayBatch:
+        """Rays of every pixel (row-major) -- or of `pixel_ids` -- on the default CUDA device, generated by K0
+        (`nerf_generate_rays`; reference View.get_rays, Datasets/utils.py:1053-1074)."""
+        from .. import ops
         device = Framework.config.GLOBAL.DEFAULT_DEVICE
-        local = self.camera.compute_local_ray_directions(device=device)
-        direction = local @ self.rotation.to(device).T
-        origin = self.position.to(device).expand_as(direction)
-        flat = lambda img: None if img is None else img.to(device).permute(1, 2, 0).reshape(direction.shape[0], -1)
-        ts = torch.full((direction.shape[0], 1), float(self.timestamp), dtype=torch.float32, device=device)
-        return RayBatch(origin=origin.contiguous(), direction=direction.contiguous(),
-                        view_direction=torch.nn.functional.normalize(direction, dim=-1),
+        cam = self.camera
+        if pixel_ids is not None:
+            pixel_ids = pixel_ids.to(device=device, dtype=torch.int64)
+        origin, direction, view_direction = ops.generate_rays(self.c2w.double().numpy(), cam.width, cam.height, cam.focal_x, cam.focal_y,
+                                                              cam.center_x, cam.center_y, pixel_ids, device)
+        n = direction.shape[0]
+
+        def flat(img):
+            if img is None:
+                return None
+            t = img.to(device).permute(1, 2, 0).reshape(cam.width * cam.height, -1)
+            return t if pixel_ids is None else t[pixel_ids]
+        ts = torch.full((n, 1), float(self.timestamp), dtype=torch.float32, device=device)
+        return RayBatch(origin=origin, direction=direction, view_direction=view_direction,
                         rgb=flat(self.rgb), alpha=flat(self.alpha), depth=flat(self.depth), timestamp=ts)

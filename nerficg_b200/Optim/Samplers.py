@@ -52,7 +52,7 @@ class DatasetSampler:
         if ray_batch_size is not None:
             ray_ids = self.img_samplers[sample_id].get(ray_batch_size).to(Framework.config.GLOBAL.DEFAULT_DEVICE)
             collection = dataset.ray_collection[self.mode]
-            ray_batch = (collection[sample_id] if collection is not None else view.get_rays())[ray_ids]
+            ray_batch = collection[sample_id][ray_ids] if collection is not None else view.get_rays(ray_ids)   # K0: only the sampled pixels
         return {'sample_id': sample_id, 'view': view, 'image_sampler': self.img_samplers[sample_id], 'ray_ids': ray_ids,
                 'ray_batch': ray_batch}
 

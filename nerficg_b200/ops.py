@@ -104,6 +104,56 @@ def loss_mse(rgb: torch.Tensor, rgb_coarse: torch.Tensor | None, alpha: torch.Te
                                ptr(background), n, float(lambda_color), float(lambda_alpha), stream_ptr()), 'nerf_loss_mse')
     return loss, g_rgb, g_rgb_c, g_alpha, g_alpha_c
 
+
+def generate_rays(c2w, width: int, height: int, focal_x: float, focal_y: float, center_x: float, center_y: float,
+                  pixel_ids: torch.Tensor | None, device: torch.device):
+    """K0 -- View.get_rays (reference src/Datasets/utils.py:1053-1074, src/Cameras/Perspective.py:64-94) for all pixels or for
+    `pixel_ids` (int64 CUDA tensor).  `c2w`: 3x4 / 4x4 camera-to-world matrix (anything numpy can read as float64).
+    Returns (origin, direction, view_direction), each (n, 3) fp32."""
+    import ctypes
+
+    import numpy as np
+    m = np.ascontiguousarray(np.asarray(c2w, dtype=np.float64))
+    if m.shape not in ((3, 4), (4, 4)):
+        raise ValueError(f'c2w must be 3x4 or 4x4, got {m.shape}')
+    if pixel_ids is not None:
+        if pixel_ids.dtype != torch.int64:
+            raise TypeError('pixel_ids must be int64')
+        pixel_ids = pixel_ids.contiguous()
+        require_device(pixel_ids)
+        n = pixel_ids.numel()
+    else:
+        n = width * height
+    out = [torch.empty((n, 3), dtype=torch.float32, device=device) for _ in range(3)]
+    require_device(out[0])
+    check(load().nerf_generate_rays(ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(pixel_ids), n,
+                                    m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(width), int(height), float(focal_x),
+                                    float(focal_y), float(center_x), float(center_y), stream_ptr()), 'nerf_generate_rays')
+    return tuple(out)
+
+
+def gather_rays(dst: dict, src: dict, ids: torch.Tensor) -> None:
+    """RayBatch.__getitem__(ids) into preallocated tensors (reference src/Datasets/utils.py:598-613), one launch.
+    `dst` / `src`: dicts with any of origin, direction, view_direction, rgb (n,3) and alpha (n,1) fp32 CUDA tensors."""
+    if ids.dtype != torch.int64:
+        raise TypeError('ids must be int64')
+    ids = ids.contiguous()
+    require_device(ids)
+    n = ids.numel()
+    args_d, args_s = [], []
+    for k in ('origin', 'direction', 'view_direction', 'rgb', 'alpha'):
+        d, s_ = dst.get(k), src.get(k)
+        if d is None or s_ is None:
+            d = s_ = None
+        else:
+            if d.dtype != torch.float32 or s_.dtype != torch.float32 or not d.is_contiguous() or not s_.is_contiguous():
+                raise TypeError(f'gather_rays: field {k} must be contiguous float32')
+            if d.shape[0] != n:
+                raise ValueError(f'gather_rays: destination {k} has {d.shape[0]} rows, expected {n}')
+        args_d.append(ptr(d))
+        args_s.append(ptr(s_))
+    check(load().nerf_gather_rays(*args_d, *args_s, ptr(ids), n, stream_ptr()), 'nerf_gather_rays')
+
 def mlp_packed_bytes() -> int:
     return int(load().nerf_mlp_packed_bytes())
 

@@ -281,3 +281,25 @@ def pinhole_rays(c2w: torch.Tensor, width: int, height: int, focal: float):
     d = local @ c2w[:3, :3].T
     o = c2w[:3, 3].expand_as(d)
     return o.contiguous(), d.contiguous(), torch.nn.functional.normalize(d, dim=-1)
+
+
+def camera_rays(c2w: torch.Tensor, width: int, height: int, focal_x: float, focal_y: float, center_x: float, center_y: float,
+                pixel_ids: Optional[torch.Tensor] = None):
+    """General pinhole camera (fx != fy, off-centre principal point): restates ``compute_local_ray_directions``
+    (src/Cameras/Perspective.py:64-94, distortion-free) + ``View.cam_to_world`` / ``View.get_rays``
+    (src/Datasets/utils.py:1033-1038, 1053-1074).  ``c2w``: 3x4 / 4x4 (float64 as the reference stores it; rotation and
+    position are cast to float32 like ``View.rotation`` / ``View.position``).  Returns origin, direction, view_direction."""
+    xs = torch.linspace((0.5 - center_x) / focal_x, (width - 1 + 0.5 - center_x) / focal_x, width)
+    ys = torch.linspace((0.5 - center_y) / focal_y, (height - 1 + 0.5 - center_y) / focal_y, height)
+    local = torch.empty((height, width, 3), dtype=torch.float32)
+    local[..., 0] = xs[None, :]
+    local[..., 1] = ys[:, None]
+    local[..., 2] = 1.0
+    local = local.reshape(-1, 3)
+    rot = c2w[:3, :3].to(torch.float32)
+    d = local @ rot.T
+    o = c2w[:3, 3].to(torch.float32).expand_as(d)
+    v = torch.nn.functional.normalize(d, dim=-1)
+    if pixel_ids is not None:
+        o, d, v = o[pixel_ids], d[pixel_ids], v[pixel_ids]
+    return o.contiguous(), d.contiguous(), v.contiguous()

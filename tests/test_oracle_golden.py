@@ -90,3 +90,14 @@ def test_lr_schedule(golden):
     g = golden('lr')
     for it, lr in zip(g['its'], g['lr']):
         assert abs(O.lr_factor(it, 5e-4, 5e-5, 500000) - lr) <= 1e-12
+
+
+def test_camera_rays(golden):
+    """Ray generation of the oracle against View.get_rays of the reference (oracle/make_golden_rays.py)."""
+    for case in golden('rays'):
+        o, d, v = O.camera_rays(case['c2w'], case['width'], case['height'], case['focal_x'], case['focal_y'], case['center_x'],
+                                case['center_y'], case['pixel_ids'])
+        assert torch.equal(o, case['origin'])
+        assert (d - case['direction']).abs().max() <= 1e-6
+        assert (v - case['view_direction']).abs().max() <= 1e-6
+        assert (v.norm(dim=-1) - 1).abs().max() <= 1e-6

@@ -191,3 +191,37 @@ def test_loss_kernel_oracle(ops, n, lam_a, coarse):
             assert (g_alpha_c.cpu() - out['alpha_coarse'].grad.reshape(-1)).abs().max() <= 1e-7
     else:
         assert g_alpha is None and g_alpha_c is None
+
+
+def test_generate_rays_golden(ops, golden):
+    """K0 against View.get_rays of the reference (tests/golden/rays.pt) and against the oracle on a third camera."""
+    for case in golden('rays'):
+        args = (case['c2w'].numpy(), case['width'], case['height'], case['focal_x'], case['focal_y'], case['center_x'], case['center_y'])
+        o, d, v = ops.generate_rays(*args, case['pixel_ids'].to(DEV), torch.device(DEV))
+        assert torch.equal(o.cpu(), case['origin'])
+        assert (d.cpu() - case['direction']).abs().max() <= 1e-6
+        assert (v.cpu() - case['view_direction']).abs().max() <= 1e-6
+        # all pixels (no id list) == the same rays in row-major order
+        o_all, d_all, v_all = ops.generate_rays(*args, None, torch.device(DEV))
+        assert d_all.shape == (case['width'] * case['height'], 3)
+        assert torch.equal(d_all[case['pixel_ids'].to(DEV)], d) and torch.equal(v_all[case['pixel_ids'].to(DEV)], v)
+    c2w = golden('rays')[0]['c2w']
+    ref = O.camera_rays(c2w, 800, 800, 1111.11, 1111.11, 400.0, 400.0)
+    got = ops.generate_rays(c2w.numpy(), 800, 800, 1111.11, 1111.11, 400.0, 400.0, None, torch.device(DEV))   # config B/C image size
+    for r, g_ in zip(ref, got):
+        assert (g_.cpu() - r).abs().max() <= 1e-6
+
+
+def test_gather_rays(ops):
+    g = torch.Generator().manual_seed(3)
+    n_pool, n = 100000, 4096
+    src = {k: torch.rand(n_pool, 3, generator=g).to(DEV) for k in ('origin', 'direction', 'view_direction', 'rgb')}
+    src['alpha'] = torch.rand(n_pool, 1, generator=g).to(DEV)
+    ids = torch.randint(0, n_pool, (n,), generator=g).to(DEV)
+    dst = {k: torch.empty((n,) + tuple(t.shape[1:]), device=DEV) for k, t in src.items()}
+    ops.gather_rays(dst, src, ids)
+    for k in src:
+        assert torch.equal(dst[k], src[k][ids]), k
+    partial = {'origin': torch.empty(n, 3, device=DEV)}
+    ops.gather_rays(partial, src, ids)                       # any subset of the fields
+    assert torch.equal(partial['origin'], src['origin'][ids])
