@@ -64,6 +64,22 @@ def run(n_rays: int = 65536, iters: int = 7, profile: bool = False, device: str 
         ts = sorted(ts[2:] if not profile else ts)
         return ts[len(ts) // 2]
 
+    # K0: all rays of one 800x800 view (36 B written per ray) and a 4096-ray batch gathered from a
+    # 64 M-ray-sized pool slice (52 B read + 52 B written per ray)
+    import numpy as np
+    c2w = np.eye(4)
+    c2w[:3, 3] = (0.0, -4.0, 0.5)
+    n_img = 800 * 800
+    t_gen = timed(lambda: ops.generate_rays(c2w, 800, 800, 1111.11, 1111.11, 400.0, 400.0, None, dev))
+    pool = {k: torch.rand(4_000_000, 3, generator=g, device=dev) for k in ('origin', 'direction', 'view_direction', 'rgb')}
+    pool['alpha'] = torch.rand(4_000_000, 1, generator=g, device=dev)
+    ids = torch.randint(0, 4_000_000, (4096,), generator=g, device=dev)
+    dst = {k: torch.empty((4096,) + tuple(t.shape[1:]), device=dev) for k, t in pool.items()}
+    t_gat = timed(lambda: ops.gather_rays(dst, pool, ids))
+    rows.append({'n_rays': n_img, 'n_coarse': 0, 'n_fine': 0, 'kernels': {
+        'K0_generate_rays_800x800': {'us': round(1e3 * t_gen, 2), 'bytes': 36 * n_img, 'gbs': round(36 * n_img / t_gen / 1e6, 1)},
+        'K0_gather_4096_rays': {'us': round(1e3 * t_gat, 2), 'bytes': 104 * 4096, 'gbs': round(104 * 4096 / t_gat / 1e6, 1)}}})
+    del pool
     for nc, nf in SWEEP:
         s = nc + nf
         u_c = torch.rand(n_rays, nc, generator=g, device=dev)
