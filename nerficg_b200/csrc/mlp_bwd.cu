@@ -20,7 +20,10 @@ using namespace tc;
 namespace bwd {
 constexpr int kEpiThreadsPerSlot = 256;  // 8 warps per slot: 4 TMEM lane quarters x 2 column halves (mlp_fwd.cu)
 constexpr int kThreads = 128 + 2 * kEpiThreadsPerSlot;
-constexpr int kRingStages = 6;                           // 16 KB stages: this CTA's 128-column half of one W^T panel (mlp_fwd.cu)
+#ifndef NERF_BWD_RING
+#define NERF_BWD_RING 6
+#endif
+constexpr int kRingStages = NERF_BWD_RING;                           // 16 KB stages: this CTA's 128-column half of one W^T panel (mlp_fwd.cu)
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 constexpr uint32_t kSlotBytes = kActBytes;
 constexpr uint32_t kOffRing = 2 * kSlotBytes;

@@ -47,7 +47,10 @@ namespace fwd {
 constexpr int kEpiThreadsPerSlot = 256;  // 8 warps: 4 TMEM lane quarters x 2 column halves
 constexpr int kThreads = 128 + 2 * kEpiThreadsPerSlot;
 // weight ring: 16 KB stages = one K panel (64 inputs) x this CTA's 128 output neurons (64 for the colour layer)
-constexpr int kRingStages = 4;
+#ifndef NERF_FWD_RING
+#define NERF_FWD_RING 4
+#endif
+constexpr int kRingStages = NERF_FWD_RING;
 constexpr uint32_t kRingStageBytes = kPanelBytes128;
 // shared memory map (offsets from the 1024-aligned base)
 constexpr uint32_t kSlotBytes = kActBytes + kPanelBytes128;  // act (4 panels) + enc (1 panel)
