@@ -239,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
     const bool prof = prof_on && tg == 0 && slot == 0;
-    long long t_accw = 0, t_drain = 0, t_pro = 0;
+    long long t_accw = 0, t_drain = 0, t_pro = 0, t_pro_compute = 0, t_pro_drain = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
@@ -281,18 +281,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         dp2 = dd.z * o.z * (1.f - o.z);
         dsr = dd.w;
       }
-      if (tile_ok) {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
-        uint8_t* hd = p.gstash + grad_region_offset(kGradHead, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(kGradHead);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {  // each half of the row writes its four 16-byte chunks
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (ch == 0 && half == 0) {
-            v.x = pack_half2(dp0, dp1);
-            v.y = pack_half2(dp2, dsr);
-          }
-          *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, 4 * half + ch)) = v;
-        }
-      }
       // dL/dg for this half's 64 of the 128 colour-layer neurons -> panel `half` (masked by g > 0).  Everything is computed
       // into registers first: the previous tile's last image store (issued moments ago) still reads act, and waiting for
       // it up front put a full store drain plus the global-load latencies on every tile's critical path.
@@ -316,7 +304,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           outw[ci][2 * q + 1] = pack_half2(m2 ? d2 : 0.f, m3 ? d3 : 0.f);
         }
       }
+      const long long t_mid = prof ? clock64() : 0;
       gstash_drain();  // previous tile's D0 store still reads act
+      if (prof) {
+        t_pro_compute += t_mid - t_tile;
+        t_pro_drain += clock64() - t_mid;
+      }
       {
         const uint32_t dpanel = act + half * kPanelBytes128;
 #pragma unroll
@@ -332,29 +325,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       __syncwarp();  // one (possibly remote) arrival per warp: per-thread remote arrivals serialise on the leader's barrier
       if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
-      // pull the next tile's prologue inputs (upstream gradients, outputs, G image) into L2 while this tile's chain runs:
-      // the prologue otherwise exposes a full HBM round trip per tile
-      if (it + 1 < n_iters && active(it + 1, slot)) {
-        const int next = group_of(it + 1, slot) * 2 + (int)rank;
-        if (next < p.n_tiles) {
-          const int64_t en = (int64_t)next * kTile + row;
-          if (half == 0 && en < p.n_evals) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_rgbsigma + en));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rgbsigma + en));
+      // (off the critical path: under 4.3 TB/s of stash stores a plain global store can stall its warp for a long time)
+      if (tile_ok) {  // head-gradient panel: cols 0..2 = dL/d(rgb pre-sigmoid), col 3 = dL/dsigma_raw, rest zero
+        uint8_t* hd = p.gstash + grad_region_offset(kGradHead, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(kGradHead);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {  // each half of the row writes its four 16-byte chunks
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (ch == 0 && half == 0) {
+            v.x = pack_half2(dp0, dp1);
+            v.y = pack_half2(dp2, dsr);
           }
-          if (tg < 32) {  // the next tile's g bits (4 KB)
-            const uint8_t* gn = p.stash + stash_region_offset(kStashMask, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashMask) +
-                                8 * (128 * 32) + tg * 128;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
-          }
+          *reinterpret_cast<uint4*>(hd + panel_chunk_offset(row, 4 * half + ch)) = v;
         }
       }
+      // Pulls the next tile's prologue inputs (upstream gradients, outputs, g bits) into L2.  Called two stages before the
+      // end of this tile's chain: issued right after the prologue (a whole tile = 35 us ahead) the lines were evicted
+      // again before their use -- the 126 MB L2 turns over every ~27 us under this kernel's 4.3 TB/s of stores -- and the
+      // prologue spent 7.4 K cycles per tile waiting for HBM.
+      auto prefetch_next_tile = [&]() {
+        if (it + 1 < n_iters && active(it + 1, slot)) {
+          const int next = group_of(it + 1, slot) * 2 + (int)rank;
+          if (next < p.n_tiles) {
+            const int64_t en = (int64_t)next * kTile + row;
+            if (half == 0 && en < p.n_evals) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_rgbsigma + en));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rgbsigma + en));
+            }
+            if (tg < 32) {  // the next tile's g bits (4 KB)
+              const uint8_t* gn = p.stash + stash_region_offset(kStashMask, n_tiles64) + (uint64_t)next * stash_region_tile_bytes(kStashMask) +
+                                  8 * (128 * 32) + tg * 128;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
+            }
+          }
+        }
+      };
 
       // ---------------- chain stages ----------------
 #pragma unroll 1
       for (int st = 0; st < kBwdStages; ++st) {
         // stage st produces the gradient w.r.t. the output of: st==0 -> f ; st>=1 -> hidden layer (8 - st)
         const int mask_layer = 8 - st;  // valid for st >= 1
+        if (st == kBwdStages - 3) prefetch_next_tile();
         uint4 mk4 = make_uint4(~0u, ~0u, ~0u, ~0u);
         if (st >= 1 && tile_ok)  // ReLU masks of this half of the row (4 words), in flight while the MMAs still run
           mk4 = __ldg(reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32)));
@@ -399,6 +410,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       atomicAdd(p.prof + 16, (unsigned long long)(clock64() - t_begin));
       atomicAdd(p.prof + 17, (unsigned long long)t_drain);
       atomicAdd(p.prof + 18, (unsigned long long)t_pro);
+      atomicAdd(p.prof + 20, (unsigned long long)t_pro_compute);  // prologue: loads + dL/dg arithmetic
+      atomicAdd(p.prof + 21, (unsigned long long)t_pro_drain);    // prologue: wait for the previous tile's last image store
     }
   }
   tc_fence_before();

@@ -441,11 +441,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       if (lane == 0) mbar_arrive_cluster(a_ready_leader);
       if (prof) t_pro += clock64() - t_tile;
 
+      // next tile's prologue inputs (depths and the ray of each sample) -> L2, issued two stages before this tile ends
+      auto prefetch_next_tile = [&]() {
+        if (half == 0 && it + 1 < n_iters && active(it + 1, slot)) {
+          const int next = group_of(it + 1, slot) * 2 + (int)rank;
+          const int64_t en = (int64_t)next * kTile + row;
+          if (next < p.n_tiles && en < p.n_evals) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.z + en));
+            if ((row & 31) == 0) {  // the 32 samples of a warp span at most two rays
+              const int rn = (int)(en / p.n_samples);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.origins + 3 * rn));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dirs + 3 * rn));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.viewdirs + 3 * rn));
+            }
+          }
+        }
+      };
       float dens = 0.f;  // density head, partial sum over this thread's 128 columns (combined in stage 9)
       // ---------------- chain stages 0..8: hidden layers (ReLU) and the feature layer (linear) ----------------
 #pragma unroll 1
       for (int st = 0; st < 9; ++st) {
         const bool relu = st < 8;
+        if (st == 7) prefetch_next_tile();
         NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
@@ -477,11 +494,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         };
         if (st == 7) run(BoolTag<true>{}); else run(BoolTag<false>{});
         bias_phase ^= 1;
-        if (kTrain && relu && tile_ok) {
-          uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
-                                               (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32 + half * 16);
-          *md = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        }
         if (st == 8) {
           // direction encoding -> enc panel (the x encoding was last read by stage 5): 27 values in half 0, zeros beyond
           float vals[32];
@@ -505,6 +517,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         tc_fence_before();
         __syncwarp();  // one (possibly remote) arrival per warp
         if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+        // ReLU bits -> stash, after the hand-off: a plain global store can stall its warp under the stash's HBM write load
+        if (kTrain && relu && tile_ok) {
+          uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
+                                               (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32 + half * 16);
+          *md = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        }
       }
       // ---------------- stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores ----------------
       {

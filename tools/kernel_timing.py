@@ -59,6 +59,9 @@ def main():
     report(buf, 0, f'forward (training)  {n_rays}x{s}', ms)
     _, ms = timed(lambda: ops.mlp_backward_dgrad(up, out, stash, ws, packed, flat, n_rays, s))
     report(buf, 10, f'dgrad               {n_rays}x{s}', ms)
+    v = buf[20:22].tolist()
+    n_cta = max(buf[19].item(), 1)
+    print(f'    prologue: loads+arithmetic {v[0] / n_cta:12.0f} cyc/CTA, store drain {v[1] / n_cta:12.0f} cyc/CTA')
     for _ in range(3):
         ops.mlp_backward_wgrad(grads, stash, ws, n_rays, s, 1024.0)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
