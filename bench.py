@@ -29,7 +29,7 @@ N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 
 METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 # algorithmic work: MACs per MLP evaluation
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
-KERNELS_PER_STEP = 17       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~27 torch elementwise / gather nodes)
+KERNELS_PER_STEP = 18       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K8 loss, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~9 torch RNG / memset / copy nodes; the bench loop adds the K0 gather when it assembles a batch)
 N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
 RENDER_VIEWS_PER_RANK = 2   # bounded sample of this rank's shard that is actually rendered and timed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
