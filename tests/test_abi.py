@@ -67,3 +67,17 @@ def test_product_package_never_imports_the_oracle():
     for path in (ROOT / 'nerficg_b200').rglob('*.py'):
         text = path.read_text()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f'{path} imports the oracle'
+
+
+def test_new_entry_points_validate_arguments_without_gpu(library):
+    """K0 / K8 argument checks return an error code and a message before any launch (no GPU needed)."""
+    import ctypes
+    lib = library.load()
+    assert lib.nerf_loss_mse(None, None, None, None, None, None, None, None, None, None, None, None, 16, 1.0, 0.0, None) != 0
+    assert b'loss_mse' in lib.nerf_last_error()
+    c2w = (ctypes.c_double * 16)(*([1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]))
+    assert lib.nerf_generate_rays(None, None, None, None, 100, c2w, 10, 10, 10.0, 10.0, 5.0, 5.0, None) != 0
+    assert b'generate_rays' in lib.nerf_last_error()
+    assert lib.nerf_generate_rays(None, None, None, None, 0, c2w, 10, 10, 10.0, 10.0, 5.0, 5.0, None) == 0   # empty batch is a no-op
+    assert lib.nerf_gather_rays(None, None, None, None, None, None, None, None, None, None, None, 0, None) == 0
+    assert lib.nerf_gather_rays(None, None, None, None, None, None, None, None, None, None, None, 8, None) != 0

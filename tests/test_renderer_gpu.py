@@ -213,7 +213,7 @@ def test_training_psnr_parity(fw):
 
         # ---- CUDA path ----
         # The weight gradients are accumulated with fp32 atomics, so two trainings differ in the last bits and, this
-        # early in training (PSNR still climbing 0.1 dB per 10 steps), end +-0.03 dB apart (tools/psnr_spread.py).
+        # early in training (PSNR still climbing 0.1 dB per 10 steps), end +-0.03 dB apart (tests/tools/psnr_spread.py).
         # (8 runs measured: mean +0.031 dB over the oracle, sigma 0.018..0.05 dB.)  The bar is therefore applied to the
         # mean of five runs; every single run must stay within 0.2 dB.
         cam = ds.default_camera

@@ -4,7 +4,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from nerficg_b200 import ops, params  # noqa: E402
 from oracle import nerf_oracle as O  # noqa: E402
 

@@ -6,7 +6,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from oracle import nerf_oracle as O  # noqa: E402
 from nerficg_b200 import Framework, ops, params  # noqa: E402
 
