@@ -200,15 +200,14 @@ class NeRFRenderer(BaseRenderer):
         return rendered
 
     def postprocess_outputs(self, outputs, view, dataset=None, index: int = 0) -> dict[str, torch.Tensor]:
-        """3xHxW images in [0,1]: clamped colour, alpha, and depth normalised to [near, far] and masked by alpha.
-        (The reference colours depth with a SPECTRAL LUT -- display-only, SURVEY 2.1 #15; grey levels are used here.)"""
-        def depth_image(depth, alpha):
-            near, far = view.camera.near_plane, view.camera.far_plane
-            return (((depth - near) / (far - near)).clamp(0, 1) * alpha).expand_as(outputs['rgb'])
+        """3xHxW images in [0,1] (reference Renderer.py:142-165): clamped colour, alpha, and depth normalised to
+        [near, far], coloured with the SPECTRAL map and masked by alpha."""
+        from ...Visual import apply_color_map
+        near_far = (view.camera.near_plane, view.camera.far_plane)
         out = {'rgb': outputs['rgb'].clamp_(0.0, 1.0), 'alpha': outputs['alpha'].expand_as(outputs['rgb']),
-               'depth': depth_image(outputs['depth'], outputs['alpha'])}
+               'depth': apply_color_map('SPECTRAL', outputs['depth'], near_far, outputs['alpha'])}
         if self.n_samples_coarse_nerf > 0:
             out |= {'rgb_coarse': outputs['rgb_coarse'].clamp_(0.0, 1.0),
                     'alpha_coarse': outputs['alpha_coarse'].expand_as(outputs['rgb_coarse']),
-                    'depth_coarse': depth_image(outputs['depth_coarse'], outputs['alpha_coarse'])}
+                    'depth_coarse': apply_color_map('SPECTRAL', outputs['depth_coarse'], near_far, outputs['alpha_coarse'])}
         return out

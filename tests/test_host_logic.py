@@ -93,3 +93,46 @@ def test_shard_range_partitions_exactly():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         dist.shard_range(10, 4, 4)
+
+
+def test_depth_color_map_matches_reference(golden):
+    """apply_color_map / SPECTRAL against the reference's own output (oracle/make_golden_postprocess.py)."""
+    from nerficg_b200.Visual import apply_color_map, spectral_lut
+    g = golden('postprocess')
+    lut = spectral_lut()
+    assert lut.shape == (256, 3) and float(lut.min()) >= 0.0 and float(lut.max()) <= 1.0
+    nf = (g['near'], g['far'])
+    assert (apply_color_map('SPECTRAL', g['depth'], nf, g['alpha']) - g['spectral_masked']).abs().max() <= 1e-6
+    assert (apply_color_map('SPECTRAL', g['depth'], None, g['alpha']) - g['spectral_auto']).abs().max() <= 1e-6
+    assert (apply_color_map('SPECTRAL', g['depth'], nf) - g['spectral_plain']).abs().max() <= 1e-6
+    assert (apply_color_map('Grayscale', g['depth'], nf, invert=True) - g['gray_inverted']).abs().max() <= 1e-6
+    import pytest
+    from nerficg_b200 import Framework
+    with pytest.raises(Framework.RendererError):
+        apply_color_map('SPECTRAL', g['depth'][0], nf)
+
+
+def test_postprocess_outputs_shapes_and_depth_coloring(cfg, golden):
+    """NeRFRenderer.postprocess_outputs (reference Renderer.py:142-165): six 3xHxW images in [0, 1]; depth = SPECTRAL over
+    [near, far] masked by alpha."""
+    from nerficg_b200.Cameras import PerspectiveCamera, SharedCameraSettings
+    from nerficg_b200.Datasets import View
+    from nerficg_b200.Methods.NeRF.Model import NeRF
+    from nerficg_b200.Methods.NeRF.Renderer import NeRFRenderer
+    import numpy as np
+    g = golden('postprocess')
+    h, w = g['depth'].shape[1:]
+    cam = PerspectiveCamera(shared_settings=SharedCameraSettings(torch.ones(3), g['near'], g['far']), width=w, height=h)
+    view = View(cam, np.eye(4))
+    r = NeRFRenderer(NeRF('t').build())
+    gen = torch.Generator().manual_seed(1)
+    rgb = torch.rand(3, h, w, generator=gen) * 1.4 - 0.2
+    outputs = {'rgb': rgb.clone(), 'alpha': g['alpha'].clone(), 'depth': g['depth'].clone(),
+               'rgb_coarse': rgb.clone(), 'alpha_coarse': g['alpha'].clone(), 'depth_coarse': g['depth'].clone()}
+    out = r.postprocess_outputs(outputs, view, None, 0)
+    assert set(out) == {'rgb', 'alpha', 'depth', 'rgb_coarse', 'alpha_coarse', 'depth_coarse'}
+    for k, v in out.items():
+        assert tuple(v.shape) == (3, h, w) and float(v.min()) >= 0.0 and float(v.max()) <= 1.0, k
+    assert torch.equal(out['rgb'], rgb.clamp(0, 1))
+    assert (out['depth'] - g['spectral_masked']).abs().max() <= 1e-6
+    assert (out['depth_coarse'] - g['spectral_masked']).abs().max() <= 1e-6
