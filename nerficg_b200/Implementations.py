@@ -41,6 +41,25 @@ class Methods:
         return Methods.import_method(method).TRAINING_INSTANCE(model=model, renderer=renderer, **kwargs)
 
 
+class Datasets:
+    """Dataset registry (reference src/Implementations.py:68-98): ``GLOBAL.DATASET_TYPE`` -> ``CustomDataset`` class."""
+    options = ('NeRF',)
+    loaded: dict[str, type] = {}
+
+    @staticmethod
+    def get_dataset_class(dataset_type: str) -> type:
+        if dataset_type not in Datasets.options:
+            raise Framework.DatasetError(f'requested invalid dataset type: {dataset_type}\navailable datasets are: {Datasets.options}')
+        if dataset_type not in Datasets.loaded:
+            Datasets.loaded[dataset_type] = importlib.import_module(f'{__package__}.Datasets.{dataset_type}').CustomDataset
+        return Datasets.loaded[dataset_type]
+
+    @staticmethod
+    def get_dataset(dataset_type: str, path: str):
+        Logger.log_info('loading dataset')
+        return Datasets.get_dataset_class(dataset_type)(path)
+
+
 def install_into_reference(reference_implementations_module) -> None:
     """Drop-in injection: makes the UNMODIFIED nerficg scripts use these classes for METHOD_TYPE 'NeRF'
     (pre-seeds the class-level module cache, src/Implementations.py:22,31-40)."""
