@@ -75,7 +75,7 @@ class BaseRenderer(Framework.Configurable, ABC):
                 main = Path(output_directory) / f'{dataset.mode}_{self.model.num_iterations_trained}'
                 for key, image in outputs.items():
                     (main / key).mkdir(parents=True, exist_ok=True)
-                    io.write_png(quantize_8bit(image).cpu(), str(main / key / f'{index:05d}.{image_extension}'), compression_level=6)
+                    io.write_png(quantize_8bit(image).cpu().contiguous(), str(main / key / f'{index:05d}.{image_extension}'), compression_level=6)
         metrics = {'PSNR': mean(psnrs)} if psnrs else {}
         if metrics and output_directory is not None:
             main = Path(output_directory) / f'{dataset.mode}_{self.model.num_iterations_trained}'

@@ -1,0 +1,49 @@
+"""GPU: the widened rows end to end on a tiny Blender-format scene on disk -- loader (f3) -> K0 ray generation / batch
+gather (f1) -> the reference's callback-driven training loop with both samplers -> test-set rendering with SPECTRAL depth
+maps, 8-bit PSNR and PNG output (f2)."""
+import math
+
+import pytest
+import torch
+
+from blender_scene import write_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_and_render_from_blender_files(tmp_path):
+    from nerficg_b200 import Framework
+    scene = tmp_path / 'scene'
+    write_scene(scene)
+    Framework.setup(None, {'RENDERER.N_SAMPLES': 48, 'RENDERER.COARSE_RATIO': 1 / 3 + 1e-7, 'RENDERER.RAY_BATCH_SIZE': 64,
+                           'TRAINING.BATCH_SIZE': 32, 'TRAINING.NUM_ITERATIONS': 6, 'DATASET.PATH': str(scene),
+                           'DATASET.BACKGROUND_COLOR': [1.0, 1.0, 1.0], 'DATASET.NORMALIZE_CUBE': None, 'GLOBAL.LOG_LEVEL': 0})
+    from nerficg_b200.Implementations import Datasets, Methods
+    dataset = Datasets.get_dataset('NeRF', str(scene))
+    assert (len(dataset.train()), len(dataset.test())) == (2, 2)
+    # rays of a view through K0 agree with its image annotations
+    view = dataset.train()[0]
+    rays = view.get_rays()
+    assert len(rays) == 48 and rays.rgb.shape == (48, 3) and rays.alpha.shape == (48, 1)
+    assert torch.equal(rays.rgb.cpu(), view.rgb.permute(1, 2, 0).reshape(48, 3))
+    ids = torch.tensor([5, 0, 47, 5], device=rays.device)
+    some = view.get_rays(ids)
+    assert torch.equal(some.direction, rays.direction[ids]) and torch.equal(some.rgb, rays.rgb[ids])
+    trainer = None
+    for single_image in (True, False):       # DatasetSampler (one view per iteration, K0 on the sampled pixels) / RayPoolSampler
+        Framework.config.TRAINING.SAMPLE_SINGLE_IMAGE = single_image
+        trainer = Methods.get_training_instance('NeRF')
+        before = {k: v.detach().clone() for k, v in trainer.model.state_dict().items()}
+        trainer.run(dataset)
+        torch.cuda.synchronize()
+        assert trainer.model.num_iterations_trained == 6
+        after = trainer.model.state_dict()
+        assert all(bool(torch.isfinite(v).all()) for v in after.values())
+        assert any(not torch.equal(before[k], after[k]) for k in before if 'frequency' not in k)
+        assert trainer._fused[32].graph is not None           # iterations 3.. replay the captured step
+    metrics = trainer.renderer.render_subset(tmp_path / 'out', dataset.test(), calculate_metrics=True, verbose=False)
+    assert math.isfinite(metrics['PSNR']) and 0.0 < metrics['PSNR'] < 60.0
+    out_dir = tmp_path / 'out' / 'test_6'
+    for key in ('rgb', 'alpha', 'depth', 'rgb_coarse', 'alpha_coarse', 'depth_coarse'):
+        assert sorted(p.name for p in (out_dir / key).iterdir()) == ['00000.png', '00001.png'], key
+    assert (out_dir / 'metrics_8bit.txt').read_text().startswith(trainer.model.model_name)
