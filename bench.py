@@ -31,7 +31,8 @@ METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
 KERNELS_PER_STEP = 18       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K8 loss, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~9 torch RNG / memset / copy nodes; the bench loop adds the K0 gather when it assembles a batch)
 N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
-RENDER_VIEWS_PER_RANK = 2   # bounded sample of this rank's shard that is actually rendered and timed
+RENDER_VIEWS_PER_RANK = 8   # bounded sample of this rank's shard that is actually rendered and timed (config C)
+SUSTAINED_SECONDS = 5.0     # extra clock-sampled run of the training step (long enough for the power governor to settle)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_mlp_summary.md), keyed like the live table
 NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
@@ -118,30 +119,80 @@ def time_cpu(n_rays: int, steps: int, warmup: int) -> float:
     return n_rays * steps / (time.perf_counter() - t0)
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use all the host threads they can."""
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    return torch.get_num_threads()
+
+
+def reference_train_step_factory(n_rays: int):
+    """The UNMODIFIED reference's own training-iteration body (src/Methods/NeRF/Trainer.py:51-63: render_rays -> NeRFLoss ->
+    backward -> Adam step) when its tree is present (/root/reference in the build container, or baseline/_ref); None otherwise
+    (the GPU box: a Python reference cannot travel, the oracle port is timed instead and labelled so)."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_root() is None:
+            return None
+        ref = ref_loader.load_reference(n_samples=N_COARSE + N_FINE, coarse_ratio=N_COARSE / (N_COARSE + N_FINE) + 1e-7)
+        from Methods.NeRF.Loss import NeRFLoss  # noqa: the reference's module
+    except Exception as e:  # noqa: BLE001
+        print(f'reference tree unusable ({type(e).__name__}: {e}); timing the oracle port', file=sys.stderr)
+        return None
+    method, DS = ref['method'], ref['ds_utils']
+    model = method.MODEL('bench').build()
+    renderer = method.RENDERER(model)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    loss_fn = NeRFLoss(1.0, 0.0, True)
+    g = torch.Generator().manual_seed(0)
+    o = torch.randn(n_rays, 3, generator=g) * 0.1 + torch.tensor([0.0, -4.0, 0.5])
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g) * 0.2 + torch.tensor([0.0, 1.0, -0.1]), dim=-1) * 1.05
+    bg = torch.ones(3)
+    rays = DS.RayBatch(origin=o, direction=d, view_direction=torch.nn.functional.normalize(d, dim=-1), rgb=torch.rand(n_rays, 3, generator=g),
+                       alpha=torch.ones(n_rays, 1))
+    cam = ref['PerspectiveCamera'](shared_settings=ref['SharedCameraSettings'](bg, 2.0, 6.0), width=WIDTH, height=HEIGHT, focal_x=1111.11, focal_y=1111.11)
+
+    def step():
+        out = renderer.render_rays(rays, cam, randomize_samples=True)
+        loss = loss_fn(out, rays, bg)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+    return step
+
+
 def run_reference_arm(args) -> None:
-    """`--impl reference`: the reference's own CPU implementation of the path = its algorithm restated in
-    oracle/nerf_oracle.py (pinned to the reference by tests/golden), all host threads, bounded sample per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores -- the unmodified reference
+    when its tree is present, else its algorithm restated in oracle/nerf_oracle.py (pinned to the reference by tests/golden);
+    all host threads, bounded sample per step."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
-    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()
     probe = 128
-    step = cpu_train_step_factory(probe)
+    kind = 'reference' if reference_train_step_factory(probe) is not None else 'port'
+    factory = reference_train_step_factory if kind == 'reference' else cpu_train_step_factory
+    step = factory(probe)
     step()
     t0 = time.perf_counter()
     step()
     per_ray = (time.perf_counter() - t0) / probe
     budget = 100.0 / max(args.steps + args.warmup, 1)           # seconds per step so the whole run stays within minutes
     n_rays = int(min(N_RAYS, max(64, budget / per_ray)))
-    value = time_cpu(n_rays, args.steps, args.warmup)
-    sample = f'{n_rays}-ray training steps ({N_COARSE}+{N_FINE} samples, fp32 PyTorch autograd + Adam) of the {N_RAYS}-ray workload'
+    step = factory(n_rays)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    value = n_rays * args.steps / (time.perf_counter() - t0)
+    what = "the unmodified reference's render_rays + NeRFLoss + Adam" if kind == 'reference' else 'fp32 PyTorch oracle port, autograd + Adam'
+    sample = f'{n_rays}-ray training steps ({N_COARSE}+{N_FINE} samples, {what}) of the {N_RAYS}-ray workload'
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * n_rays / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
         'data': 'synthetic', 'config': workload_config(args.gpus),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
 
 
@@ -281,38 +332,66 @@ def run_gpu_arm(args) -> None:
     value = N_RAYS * world * args.steps / (elapsed_ms * 1e-3)
     e2e_value = N_RAYS * world * args.steps / (e2e_ms * 1e-3)
 
-    # ---- rendering throughput (second half of the metric; config C): the 200 test views are sharded across ranks by
-    # view (dist.shard_range, no collective); every rank renders a bounded sample of ITS shard ----
+    # ---- sustained clocks: the same step for >= SUSTAINED_SECONDS with nvidia-smi sampling (the K-step region above is too
+    # short for the power governor to settle; this is the number a long training run sees) ----
+    n_sus = max(int(SUSTAINED_SECONDS * 1e3 / (elapsed_ms / args.steps)), args.steps)
+    sync_all()
+    with ClockSampler(local_rank) as sus_clocks:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            trainer.fused_step(batches[i % len(batches)], camera)
+        s1.record()
+        sync_all()
+        sus_ms = s0.elapsed_time(s1)
+    if world > 1:
+        t = torch.tensor([sus_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        sus_ms = t.item()
+    sustained = {'steps': n_sus, 'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / n_sus, 'value': N_RAYS * world * n_sus / (sus_ms * 1e-3),
+                 'unit': UNIT, 'clocks': sus_clocks.summary()}
+
+    # ---- config C, rendering throughput (second half of the metric): the 200 test views are sharded across ranks by view
+    # (dist.shard_range, no collective); every rank renders a bounded sample of ITS shard through the public call
+    # NeRFRenderer.render_image(view) -- K0 ray generation inside the timed region, one full-size warm-up view outside ----
     from nerficg_b200 import dist
     shard = dist.shard_range(N_TEST_VIEWS, rank, world)
     test_views = dataset.test()
     my_views = [test_views[i % len(test_views)] for i in list(shard)[:RENDER_VIEWS_PER_RANK]]
     dataset.train()
+    del batches, host
+    trainer._fused.clear()           # the training stashes (9.5 GB) are not needed any more
+    view_ms = []
     with torch.no_grad():
         renderer.RAY_BATCH_SIZE = 65536
-        ray_sets = [v.get_rays() for v in my_views]
-        renderer.render_rays(ray_sets[0][:65536], my_views[0].camera)
+        model.eval()
+        renderer.render_image(my_views[0])               # full-size warm-up view (allocator, lazy module loads)
         sync_all()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for v, rays in zip(my_views, ray_sets):
-            renderer.render_rays(rays, v.camera)
-        r1.record()
-        sync_all()
-        render_ms = r0.elapsed_time(r1)
-    n_render_rays = sum(len(r) for r in ray_sets)
+        with ClockSampler(local_rank) as render_clocks:
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(my_views) + 1)]
+            marks[0].record()
+            n_render_rays = 0
+            for i, v in enumerate(my_views):
+                out = renderer.render_image(v)
+                n_render_rays += out['rgb'].shape[0] * out['rgb'].shape[1]
+                marks[i + 1].record()
+            sync_all()
+        render_ms = marks[0].elapsed_time(marks[-1])
+        view_ms = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(len(my_views))]
     if world > 1:
         t = torch.tensor([render_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         render_ms = t.item()
     render_mrays = n_render_rays * world / (render_ms * 1e-3) / 1e6
+    render_tflops = FLOP_FWD * (N_COARSE + N_COARSE + N_FINE) * n_render_rays * world / render_ms / 1e9
 
     if rank != 0:
         _leave(world)   # the remaining work (per-kernel table, CPU baseline) is rank 0's alone and uses no collective
 
     # ---- per-kernel roofline (rank 0): live CUDA-event timing of every launch of one iteration ----
     peaks, peak_source = measured_peaks()
-    kt = instrumented_kernel_times(trainer, trainer._fused[N_RAYS])
+    trainer.fused_step(device_batch(), camera)
+    kt = instrumented_kernel_times(trainer, next(iter(trainer._fused.values())))
     evals = {'coarse': N_RAYS * N_COARSE, 'fine': N_RAYS * (N_COARSE + N_FINE)}
     n_tiles = {k: (v + 127) // 128 for k, v in evals.items()}
     table = {}
@@ -355,7 +434,7 @@ def run_gpu_arm(args) -> None:
             k['frac'] = round(k['gbs'] / peaks['hbm_gbs'], 3)
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()     # (torchrun exports OMP_NUM_THREADS=1)
     cpu_rays = 1024
     cpu_value = time_cpu(cpu_rays, steps=3, warmup=1)
     cpu_baseline = {'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
@@ -369,9 +448,13 @@ def run_gpu_arm(args) -> None:
                 'last_loss': losses[-1]},
         'gpu_launches': KERNELS_PER_STEP * args.steps, 'clocks': clocks.summary(),
         'roofline': roofline, 'kernels': table, 'cpu_baseline': cpu_baseline,
-        'render': {'metric': 'nerf_render_mrays_per_s', 'value': render_mrays, 'unit': 'Mrays/s', 'rays_per_gpu': n_render_rays,
-                   'views_per_gpu_timed': len(my_views), 'views_in_shard': len(shard), 'ms': render_ms,
-                   'tensor_tflops': FLOP_FWD * (N_COARSE + N_COARSE + N_FINE) * n_render_rays * world / render_ms / 1e9},
+        'sustained': sustained,
+        'render': {'metric': 'nerf_render_mrays_per_s', 'value': render_mrays, 'unit': 'Mrays/s', 'n_gpus': world,
+                   'workload': f'config C: {N_TEST_VIEWS} test views {WIDTH}x{HEIGHT} sharded by view over {world} rank(s), no collective; '
+                               f'{len(my_views)} views of each rank\'s shard timed through NeRFRenderer.render_image (K0 ray generation inside), {N_COARSE}+{N_FINE} samples',
+                   'rays_per_gpu': n_render_rays, 'views_per_gpu_timed': len(my_views), 'views_in_shard': len(shard), 'ms': render_ms,
+                   'ms_per_view_rank0': view_ms, 'per_gpu_mrays': render_mrays / world, 'tensor_tflops': render_tflops,
+                   'tensor_frac_of_burst_peak_per_gpu': render_tflops / world / peaks['bf16_tflops'], 'clocks': render_clocks.summary()},
         'stress': stress,
     }), flush=True)
     _leave(world)

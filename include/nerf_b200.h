@@ -119,6 +119,11 @@ int nerf_mlp_backward_wgrad(float* grads, const void* stash, const void* workspa
 int nerf_adam_tick(float* state, float beta1, float beta2, void* stream);
 int nerf_adam_update(float* params, float* exp_avg, float* exp_avg_sq, const float* grads, const float* lr, const float* state,
                      float beta1, float beta2, float eps, int64_t n, void* stream);
+/* Same update with the gradient multiplied by `grad_mult` on the fly (1/world_size of the data-parallel mean: the NCCL
+ * all-reduce stays a plain SUM) and, when zero_grads != 0, the gradient buffer cleared behind the read
+ * (optimizer.zero_grad(), src/Methods/NeRF/Trainer.py:62). */
+int nerf_adam_update_ex(float* params, float* exp_avg, float* exp_avg_sq, float* grads, const float* lr, const float* state,
+                        float beta1, float beta2, float eps, float grad_mult, int zero_grads, int64_t n, void* stream);
 
 /* K8 -- NeRFLoss.forward and its gradient in one launch (reference src/Methods/NeRF/Loss.py:26-43,
  * src/Datasets/utils.py:185-189, src/Optim/Losses/utils.py:54-57):

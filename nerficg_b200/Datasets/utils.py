@@ -173,11 +173,17 @@ class View:
                                                               cam.center_x, cam.center_y, pixel_ids, device)
         n = direction.shape[0]
 
-        def flat(img):
+        def flat(name):
+            img = getattr(self, name)
             if img is None:
                 return None
-            t = img.to(device).permute(1, 2, 0).reshape(cam.width * cam.height, -1)
-            return t if pixel_ids is None else t[pixel_ids]
+            # the (H*W, C) device copy is made once per view and kept: re-uploading the whole image every training
+            # iteration was 10 MB of H2D per step at 800x800 (the sampled rows are then one device gather)
+            cache = self.__dict__.setdefault('_flat_device_cache', {})
+            hit = cache.get(name)
+            if hit is None or hit[0] is not img or hit[1].device != torch.device(device):
+                hit = cache[name] = (img, img.to(device).permute(1, 2, 0).reshape(cam.width * cam.height, -1).contiguous())
+            return hit[1] if pixel_ids is None else hit[1][pixel_ids]
         ts = torch.full((n, 1), float(self.timestamp), dtype=torch.float32, device=device)
         return RayBatch(origin=origin, direction=direction, view_direction=view_direction,
-                        rgb=flat(self.rgb), alpha=flat(self.alpha), depth=flat(self.depth), timestamp=ts)
+                        rgb=flat('rgb'), alpha=flat('alpha'), depth=flat('depth'), timestamp=ts)

@@ -5,6 +5,13 @@ the same YAML files / ``KEY=VAL`` overrides), the ``Configurable.configure`` cla
 copies UPPERCASE defaults + config-section overrides onto instances (Framework.py:73-108), the
 exception hierarchy (Framework.py:360-428), seeding and device setup.  There is no CPU mode here:
 ``setup_torch`` selects ``cuda:GPU_INDICES[0]`` or raises.
+
+Drop-in mode: the reference keeps its configuration in the module global ``Framework.config`` and REBINDS it in
+``load_config`` (Framework.py:163-176), and every ``Configurable`` reads that global at construction
+(Framework.py:73-88).  ``bind_host_framework(reference_Framework_module)`` (called by
+``Implementations.install_into_reference``) makes ``nerficg_b200.Framework.config`` / ``.Directories`` resolve to
+the host module's objects at every access (module ``__getattr__``), so the host run's YAML sections,
+``KEY=VAL`` overrides, ``GLOBAL.DEFAULT_DEVICE`` and output directories are the ones our plugin classes see.
 """
 from __future__ import annotations
 
@@ -59,7 +66,7 @@ class ConfigParameterList(dict):
                 self[key] = value.copy() if isinstance(value, ConfigParameterList) else value
 
 
-class Directories:
+class _LocalDirectories:
     ROOT: Path = Path(__file__).resolve().parent.parent
     NERFICG_ROOT: Path = ROOT
     OUTPUT_DIR: Path = ROOT / 'output'
@@ -71,8 +78,45 @@ def get_default_global_config() -> ConfigParameterList:
                                FILTER_WARNINGS=True, METHOD_TYPE='NeRF', DATASET_TYPE='NeRF')
 
 
-config: ConfigParameterList = ConfigParameterList(GLOBAL=get_default_global_config(),
-                                                  TRAINING=ConfigParameterList(WANDB=ConfigParameterList(ACTIVATE=False)))
+_local_config: ConfigParameterList = ConfigParameterList(GLOBAL=get_default_global_config(),
+                                                         TRAINING=ConfigParameterList(WANDB=ConfigParameterList(ACTIVATE=False)))
+_host = None  # the reference's Framework module once bound (drop-in mode)
+
+
+def bind_host_framework(host_framework_module) -> None:
+    """Drop-in mode: resolve ``config`` and ``Directories`` through the host framework's module from now on."""
+    global _host
+    if not hasattr(host_framework_module, 'Configurable') or not hasattr(host_framework_module, 'Directories'):
+        raise FrameworkError(f'{host_framework_module!r} is not a nerficg Framework module')
+    _host = host_framework_module
+
+
+def unbind_host_framework() -> None:
+    global _host
+    _host = None
+
+
+def host_framework():
+    return _host
+
+
+def current_config():
+    """The live configuration: the host framework's ``config`` global when bound (looked up at every call because the
+    host rebinds it in load_config / deletes it in teardown), else this module's own."""
+    if _host is not None:
+        cfg = getattr(_host, 'config', None)
+        if cfg is None:
+            raise FrameworkError('host framework is bound but has no config loaded (call its Framework.setup() first)')
+        return cfg
+    return _local_config
+
+
+def __getattr__(name: str):  # PEP 562: Framework.config / Framework.Directories are resolved at access time
+    if name == 'config':
+        return current_config()
+    if name == 'Directories':
+        return _host.Directories if _host is not None else _LocalDirectories
+    raise AttributeError(f'module {__name__!r} has no attribute {name!r}')
 
 
 class Configurable:
@@ -83,11 +127,13 @@ class Configurable:
     def __init__(self, config_file_data_field: str) -> None:
         self.config_file_data_field = config_file_data_field
         params = type(self)._configuration.copy()
-        section = config.get(config_file_data_field)
+        cfg = current_config()
+        section = cfg.get(config_file_data_field) if hasattr(cfg, 'get') else getattr(cfg, config_file_data_field, None)
         if section is None:
             Logger.log_debug(f'config section {config_file_data_field} missing for {type(self).__name__}: using defaults')
         else:
-            params.recursive_update(section if isinstance(section, ConfigParameterList) else ConfigParameterList.fromDict(section))
+            # the host framework's sections are Munch objects: converted (recursively) to our container
+            params.recursive_update(section if isinstance(section, ConfigParameterList) else ConfigParameterList.fromDict(dict(section)))
         for key in params:
             self.__dict__[key] = params[key]
 
@@ -115,13 +161,16 @@ class Configurable:
 def load_config(config_path: Path | str | None, overrides: dict[str, Any] | None = None) -> ConfigParameterList:
     """YAML -> global ``config``; ``overrides`` are dotted ``A.B.C`` keys (strings are literal_eval'ed),
     the reference's ``-c cfg.yaml KEY=VAL`` mechanism (Framework.py:163-199)."""
-    global config
+    global _local_config
+    if _host is not None:
+        raise FrameworkError('a host framework is bound: load the configuration through the host\'s Framework.setup()')
     if config_path is not None:
         with open(config_path) as f:
             config = ConfigParameterList.fromDict(yaml.safe_load(f))
         config.path = Path(config_path)
     else:
         config = ConfigParameterList(GLOBAL=get_default_global_config())
+    _local_config = config
     defaults = get_default_global_config()
     config.setdefault('GLOBAL', ConfigParameterList())
     for k, v in defaults.items():
@@ -147,6 +196,7 @@ def load_config(config_path: Path | str | None, overrides: dict[str, Any] | None
 
 
 def set_random_seed() -> None:
+    config = current_config()
     if config.GLOBAL.RANDOM_SEED is None:
         config.GLOBAL.RANDOM_SEED = int(np.random.randint(0, 2 ** 31 - 1))
     torch.manual_seed(config.GLOBAL.RANDOM_SEED)
@@ -159,6 +209,7 @@ def setup_torch(device_index: int | None = None) -> torch.device:
     from . import _lib
     if not torch.cuda.is_available():
         raise FrameworkError('nerficg_b200 needs a B200 GPU: CUDA is not available and there is no CPU path')
+    config = current_config()
     if device_index is None:
         indices = config.GLOBAL.GPU_INDICES or [0]
         device_index = indices[0]

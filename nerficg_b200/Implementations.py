@@ -36,6 +36,8 @@ class Methods:
     @staticmethod
     def get_training_instance(method: str, checkpoint: str | None = None, **kwargs):
         Logger.log_info('creating training instance')
+        if checkpoint is not None:  # '.train' resume (reference src/Implementations.py:61-62, Base/Trainer.py:94-104)
+            return Methods.import_method(method).TRAINING_INSTANCE.load(checkpoint)
         model = Methods.get_model(method, name=Framework.config.TRAINING.get('MODEL_NAME', 'Default'))
         renderer = Methods.get_renderer(method, model)
         return Methods.import_method(method).TRAINING_INSTANCE(model=model, renderer=renderer, **kwargs)
@@ -60,7 +62,24 @@ class Datasets:
         return Datasets.get_dataset_class(dataset_type)(path)
 
 
-def install_into_reference(reference_implementations_module) -> None:
-    """Drop-in injection: makes the UNMODIFIED nerficg scripts use these classes for METHOD_TYPE 'NeRF'
-    (pre-seeds the class-level module cache, src/Implementations.py:22,31-40)."""
+def install_into_reference(reference_implementations_module, reference_framework_module=None) -> None:
+    """Drop-in injection: makes the UNMODIFIED nerficg scripts use these classes for METHOD_TYPE 'NeRF'.
+
+    1. binds ``nerficg_b200.Framework.config`` / ``Directories`` to the host's ``Framework`` module, so our
+       ``Configurable`` classes read the host run's YAML sections and ``KEY=VAL`` overrides, ``GLOBAL.DEFAULT_DEVICE``
+       and output directories (reference src/Framework.py:73-108,163-199,263-290);
+    2. pre-seeds the class-level module cache (src/Implementations.py:22,31-40) so that ``get_model`` /
+       ``get_renderer`` / ``get_training_instance`` resolve METHOD_TYPE 'NeRF' to this package.
+    """
+    if reference_framework_module is None:
+        reference_framework_module = getattr(reference_implementations_module, 'Framework', None)
+    if reference_framework_module is None:
+        raise Framework.FrameworkError('install_into_reference: the reference Implementations module exposes no Framework module')
+    Framework.bind_host_framework(reference_framework_module)
     reference_implementations_module.Methods.modules['NeRF'] = Methods.import_method('NeRF')
+
+
+def uninstall_from_reference(reference_implementations_module) -> None:
+    """Undo install_into_reference (tests)."""
+    reference_implementations_module.Methods.modules.pop('NeRF', None)
+    Framework.unbind_host_framework()

@@ -46,6 +46,11 @@ class BaseModel(Framework.Configurable, ABC, torch.nn.Module):
             checkpoint = torch.load(path, map_location=map_location, weights_only=False)
         except IOError as e:
             raise Framework.ModelError(f'failed to load model from file: "{e}"')
+        return cls.from_checkpoint_dict(checkpoint)
+
+    @classmethod
+    def from_checkpoint_dict(cls, checkpoint: dict) -> 'BaseModel':
+        """Rebuilds a model from the dict ``save`` writes -- the reference's checkpoint format (Base/Model.py:60-111)."""
         model = cls()
         for key in _META + list(cls.get_default_parameters().keys()):
             if key in checkpoint:
@@ -61,11 +66,14 @@ class BaseModel(Framework.Configurable, ABC, torch.nn.Module):
         device = Framework.config.GLOBAL.get('DEFAULT_DEVICE')
         return model.to(device) if device is not None else model
 
+    def checkpoint_dict(self) -> dict:
+        checkpoint = {'model_state_dict': self.state_dict()}
+        for key in _META + list(type(self).get_default_parameters().keys()):
+            checkpoint[key] = self.__dict__[key]
+        return checkpoint
+
     def save(self, path: Path) -> None:
         try:
-            checkpoint = {'model_state_dict': self.state_dict()}
-            for key in _META + list(type(self).get_default_parameters().keys()):
-                checkpoint[key] = self.__dict__[key]
-            torch.save(checkpoint, path)
+            torch.save(self.checkpoint_dict(), path)
         except IOError as e:
             Logger.log_warning(f'failed to save model: "{e}"')

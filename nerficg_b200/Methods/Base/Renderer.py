@@ -18,7 +18,7 @@ from .Model import BaseModel
 class BaseRenderingComponent(ABC, torch.nn.Module):
     """Sub-component that executes the model.  The reference wraps it in ``torch.nn.DataParallel`` for several
     GPU_INDICES, which cannot scatter a RayBatch (its own FIXME, NeRF/Renderer.py:31); here multi-GPU is one
-    process per GPU (nerficg_b200/distributed.py), so ``get`` is a plain constructor."""
+    process per GPU (nerficg_b200/dist.py), so ``get`` is a plain constructor."""
 
     @classmethod
     def get(cls, *args) -> 'BaseRenderingComponent':

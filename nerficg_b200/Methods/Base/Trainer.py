@@ -37,6 +37,48 @@ class BaseTrainer(Framework.Configurable, torch.nn.Module):
         if write_outputs:
             self.checkpoint_directory.mkdir(parents=True, exist_ok=True)
 
+    # ---- '.train' checkpoints (reference Base/Trainer.py:94-111) -------------------------------------------
+    # The reference pickles the whole trainer object.  Ours owns CUDA graphs and ctypes handles, so the file holds the
+    # state needed to resume instead: model checkpoint dict, optimiser state_dict (torch.optim.Adam layout), schedule
+    # position and the TRAINING parameters; ``load`` rebuilds model -> renderer -> trainer from it.
+    @classmethod
+    def _method_classes(cls) -> tuple[type, type]:
+        raise Framework.CheckpointError(f'{cls.__name__} does not define its MODEL / RENDERER classes')
+
+    def save(self, path: Path) -> None:
+        try:
+            state = {'format': 'nerficg_b200.train/1', 'trainer_class': type(self).__name__,
+                     'model': self.model.checkpoint_dict(),
+                     'optimizer': self.optimizer.state_dict() if hasattr(self, 'optimizer') else None,
+                     'training_parameters': {k: (v.toDict() if isinstance(v, Framework.ConfigParameterList) else v)
+                                             for k, v in self.__dict__.items() if k in type(self).get_default_parameters()}}
+            torch.save(state, path)
+        except IOError as e:
+            raise Framework.CheckpointError(f'Failed to save checkpoint "{e}"')
+
+    @classmethod
+    def load(cls, checkpoint_name: str | Path) -> 'BaseTrainer':
+        if checkpoint_name is None or str(checkpoint_name).split('.')[-1] != 'train':
+            raise Framework.CheckpointError(f'Invalid checkpoint name "{checkpoint_name}"')
+        try:
+            path = Path(checkpoint_name)
+            if not path.is_absolute():
+                path = Framework.Directories.NERFICG_ROOT / path
+            state = torch.load(path, map_location='cpu', weights_only=False)
+        except IOError as e:
+            raise Framework.CheckpointError(f'Failed to load checkpoint "{e}"')
+        if not isinstance(state, dict) or state.get('format') != 'nerficg_b200.train/1':
+            raise Framework.CheckpointError(f'"{checkpoint_name}" is not a nerficg_b200 training checkpoint (a pickled reference '
+                                            'trainer cannot be resumed on the CUDA path; load its model checkpoint instead)')
+        model_cls, renderer_cls = cls._method_classes()
+        model = model_cls.from_checkpoint_dict(state['model'])
+        trainer = cls(model=model, renderer=renderer_cls(model))
+        for key, value in state['training_parameters'].items():   # the run that is resumed keeps its own hyper-parameters
+            trainer.__dict__[key] = Framework.ConfigParameterList.fromDict(value) if isinstance(value, dict) else value
+        if state.get('optimizer') is not None and hasattr(trainer, 'optimizer'):
+            trainer.optimizer.load_state_dict(state['optimizer'])
+        return trainer
+
     def _callbacks(self, callback_type: int) -> list[Callable]:
         found = []
         for _, fn in inspect.getmembers(type(self), predicate=inspect.isfunction):

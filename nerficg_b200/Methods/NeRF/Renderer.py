@@ -15,6 +15,7 @@ import os
 import torch
 
 from ... import Framework, ops, params
+from ...profiling import stage
 from ...Cameras.Perspective import PerspectiveCamera
 from ...Datasets.utils import RayBatch, View
 from ...Logging import Logger
@@ -65,18 +66,25 @@ class _RenderChunk(torch.autograd.Function):
         outs = []
         need = st.need_grad
         if st.n_coarse > 0:
-            z_c = ops.sample_stratified(n, st.n_coarse, st.near, st.far, u_c, dev)
+            with stage('K1 stratified'):
+                z_c = ops.sample_stratified(n, st.n_coarse, st.near, st.far, u_c, dev)
             stash_c = torch.empty(ops.mlp_stash_bytes(n * st.n_coarse), dtype=torch.uint8, device=dev) if need else None
-            rs_c = ops.mlp_forward(st.packed_c, st.flat_c, origin, direction, view_direction, z_c, noise_c, stash_c)
-            rgb_c, depth_c, alpha_c, w_c = ops.composite_forward(z_c, rs_c, direction, st.background, want_weights=True)
-            z = ops.sample_importance(z_c, w_c, st.n_fine, u_f)
+            with stage('K3 mlp_fwd coarse'):
+                rs_c = ops.mlp_forward(st.packed_c, st.flat_c, origin, direction, view_direction, z_c, noise_c, stash_c)
+            with stage('K5 composite coarse'):
+                rgb_c, depth_c, alpha_c, w_c = ops.composite_forward(z_c, rs_c, direction, st.background, want_weights=True)
+            with stage('K2 importance+merge'):
+                z = ops.sample_importance(z_c, w_c, st.n_fine, u_f)
             outs = [rgb_c, depth_c, alpha_c]
         else:
-            z = ops.sample_stratified(n, st.n_fine, st.near, st.far, u_f, dev)
+            with stage('K1 stratified'):
+                z = ops.sample_stratified(n, st.n_fine, st.near, st.far, u_f, dev)
             z_c = rs_c = stash_c = None
         stash_f = torch.empty(ops.mlp_stash_bytes(z.numel()), dtype=torch.uint8, device=dev) if need else None
-        rs_f = ops.mlp_forward(st.packed_f, st.flat_f, origin, direction, view_direction, z, noise_f, stash_f)
-        rgb, depth, alpha, _ = ops.composite_forward(z, rs_f, direction, st.background)
+        with stage('K3 mlp_fwd fine'):
+            rs_f = ops.mlp_forward(st.packed_f, st.flat_f, origin, direction, view_direction, z, noise_f, stash_f)
+        with stage('K5 composite fine'):
+            rgb, depth, alpha, _ = ops.composite_forward(z, rs_f, direction, st.background)
         if need:
             ctx.saved = (direction, z_c, rs_c, stash_c, z, rs_f, stash_f)
         return (rgb, depth, alpha, *outs)
@@ -98,8 +106,10 @@ class _RenderChunk(torch.autograd.Function):
                 return grad
             gr = torch.zeros(n, 3, device=zz.device) if gr is None else gr
             flatten = lambda t: None if t is None else t.reshape(-1)
-            d_rs = ops.composite_backward(zz, rs, direction, st.background, gr, flatten(gd), flatten(ga), True, scale)
-            ops.mlp_backward(grad, d_rs, rs, stash, ws, packed, flat, n, zz.shape[1], scale)
+            with stage('K6 composite_bwd'):
+                d_rs = ops.composite_backward(zz, rs, direction, st.background, gr, flatten(gd), flatten(ga), True, scale)
+            with stage('K4 mlp_bwd (dgrad + wgrad)'):
+                ops.mlp_backward(grad, d_rs, rs, stash, ws, packed, flat, n, zz.shape[1], scale)
             return grad
 
         grads = []
@@ -192,7 +202,9 @@ class NeRFRenderer(BaseRenderer):
                                             self.n_samples_nerf, randomize_samples, random_noise_density, noise)
 
     def render_image(self, view: View, to_chw: bool = False, benchmark: bool = False) -> dict[str, torch.Tensor]:
-        rendered = self.render_rays(view.get_rays(), view.camera)
+        with stage('K0 generate_rays'):
+            rays = view.get_rays()
+        rendered = self.render_rays(rays, view.camera)
         for key in rendered:
             rendered[key] = rendered[key].reshape(view.camera.height, view.camera.width, -1)
             if to_chw:

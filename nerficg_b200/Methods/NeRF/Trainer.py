@@ -15,6 +15,7 @@ import torch
 
 from ... import Framework, dist, ops, params
 from ...Logging import Logger
+from ...profiling import stage
 from ...Optim.FlatAdam import FlatAdam
 from ...Optim.lr_utils import LRDecayPolicy
 from ...Optim.Samplers import DatasetSampler, RandomImageSampler, RayPoolSampler
@@ -53,7 +54,16 @@ class NeRFTrainer(BaseTrainer):
         self.loss = NeRFLoss(self.LAMBDA_COLOR_LOSS, self.LAMBDA_ALPHA_LOSS, self.model.coarse_nerf is not None)
         self.sampler_train = None
         self.sampler_val = None
-        self._fused: dict[int, '_FusedStep'] = {}
+        self._fused: dict[tuple, '_FusedStep'] = {}
+        # data parallel: every rank starts from rank 0's weights whatever its own seed drew
+        if dist.world_size() > 1:
+            dist.broadcast_parameters_([b.flat_params for b in self.model.blocks()])
+
+    @classmethod
+    def _method_classes(cls):
+        from .Model import NeRF
+        from .Renderer import NeRFRenderer
+        return NeRF, NeRFRenderer
 
     @pre_training_callback(priority=1000)
     @torch.no_grad()
@@ -78,6 +88,8 @@ class NeRFTrainer(BaseTrainer):
                                             random_noise_density=self.DENSITY_RANDOM_NOISE_STD)
         loss = self.loss(outputs, ray_batch, camera.background_color)
         loss.backward()
+        if dist.world_size() > 1:   # the autograd path exchanges gradients too (one all-reduce per parameter tensor)
+            dist.allreduce_mean_([p.grad for p in self.model.parameters() if p.grad is not None])
         self.optimizer.step()
         self.optimizer.zero_grad()
         self.lr_scheduler.step()
@@ -96,10 +108,17 @@ class NeRFTrainer(BaseTrainer):
     def fused_step(self, ray_batch, camera, use_graph: bool = True) -> torch.Tensor:
         """One full training iteration on ``ray_batch`` (single chunk).  Returns the loss as a device scalar."""
         n = len(ray_batch)
-        step = self._fused.get(n)
+        # everything a captured step freezes is part of the key; at most two steps (each owns a multi-GB stash and a graph) are kept
+        key = (n, float(camera.near_plane), float(camera.far_plane), tuple(float(c) for c in camera.background_color.flatten().tolist()),
+               float(self.LAMBDA_COLOR_LOSS), float(self.LAMBDA_ALPHA_LOSS), float(self.DENSITY_RANDOM_NOISE_STD), bool(use_graph))
+        step = self._fused.get(key)
         if step is None:
-            step = self._fused[n] = _FusedStep(self, n, camera, use_graph)
+            while len(self._fused) >= 2:
+                self._fused.pop(next(iter(self._fused)))
+            step = self._fused[key] = _FusedStep(self, n, camera, use_graph)
         loss = step.run(ray_batch)
+        if self.loss.activate_logging:   # the fused step bypasses the loss module: keep its running averages fed
+            self.loss.log_fused(float(loss))
         self.lr_scheduler.step()
         return loss
 
@@ -159,6 +178,12 @@ class _FusedStep:
             trainer.optimizer.bind_flat_grads(self.grads)
         self.scale = default_grad_scale(n_rays)
         self.world = dist.world_size()
+        self.flat_adam = isinstance(trainer.optimizer, FlatAdam)
+        if self.flat_adam:
+            # K7 reads grad * 1/world (the NCCL exchange stays a plain SUM) and clears the buffers behind the read
+            trainer.optimizer.grad_mult = 1.0 / self.world
+            trainer.optimizer.zero_bound_grads = True
+        self.side_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.graph = None
         self.use_graph = use_graph
         self.calls = 0
@@ -169,6 +194,10 @@ class _FusedStep:
                 p.grad = view
 
     def _body(self) -> None:
+        with stage('training step (K1..K8)'):
+            self._body_impl()
+
+    def _body_impl(self) -> None:
         t, n, dev = self.t, self.n, self.dev
         flats = [b.flat_params for b in self.blocks]
         for flat, packed in zip(flats, self.packed):
@@ -195,14 +224,29 @@ class _FusedStep:
         _, g_rgb, g_rgb_c, g_alpha, g_alpha_c = ops.loss_mse(
             rgb, rgb_c if coarse else None, alpha.reshape(-1), alpha_c.reshape(-1) if coarse else None, self.rgb_gt,
             self.alpha_gt.reshape(-1), self.bg, lc, la, loss_out=self.loss_out)
-        for g in self.grads:
-            g.zero_()
+        if not self.flat_adam:      # (K7 leaves the flat gradient buffers zeroed behind its read)
+            for g in self.grads:
+                g.zero_()
         d_rs = ops.composite_backward(z, rs_f, self.direction, self.bg, g_rgb, None, g_alpha, True, self.scale)
         ops.mlp_backward(self.grads[fine], d_rs, rs_f, self.stash[fine], self.ws, self.packed[fine], flats[fine], n, z.shape[1], self.scale)
+        if self.world > 1 and coarse:
+            # the fine network's gradients are reduced over NVLink while the coarse backward runs
+            main = torch.cuda.current_stream()
+            self.side_stream.wait_stream(main)
+            with torch.cuda.stream(self.side_stream):
+                dist.allreduce_sum_([self.grads[fine]])
         if coarse:
             d_rs_c = ops.composite_backward(z_c, rs_c, self.direction, self.bg, g_rgb_c, None, g_alpha_c, True, self.scale)
             ops.mlp_backward(self.grads[0], d_rs_c, rs_c, self.stash[0], self.ws, self.packed[0], flats[0], n, self.nc, self.scale)
-        dist.allreduce_mean_(self.grads)
+        if self.world > 1:
+            if coarse:
+                dist.allreduce_sum_([self.grads[0]])
+                torch.cuda.current_stream().wait_stream(self.side_stream)
+            else:
+                dist.allreduce_sum_(self.grads)
+            if not self.flat_adam:
+                for g in self.grads:
+                    g.mul_(1.0 / self.world)
         t.optimizer.step()
 
     @torch.no_grad()

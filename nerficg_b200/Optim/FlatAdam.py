@@ -25,6 +25,8 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg_sq = [torch.zeros_like(f) for f in flats]
         self.device_state = torch.zeros(4, dtype=torch.float32, device=device)   # {step, 1-b1^t, sqrt(1-b2^t), -}
         self._flat_grads: list[torch.Tensor | None] = [None] * len(self.blocks)
+        self.grad_mult = 1.0          # folded into the gradient read (1/world_size under data parallelism)
+        self.zero_bound_grads = False  # clear the bound flat gradient buffers behind the read (zero_grad folded into the step)
 
     def bind_flat_grads(self, grads: list[torch.Tensor]) -> None:
         """Registers the flat gradient buffers the fused training step accumulates into (parameter .grad fields are
@@ -53,11 +55,13 @@ class FlatAdam(torch.optim.Optimizer):
             flat = block.flat_params
             g = self._flat_grads[i]
             first = block.ordered_parameters()[0]
-            if g is None or first.grad is None or first.grad.data_ptr() != g.data_ptr():
+            bound = g is not None and first.grad is not None and first.grad.data_ptr() == g.data_ptr()
+            if not bound:
                 g = self._gather_grad(i)
-            _lib.check(lib.nerf_adam_update(flat.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(), g.data_ptr(),
-                                            lr.data_ptr(), self.device_state.data_ptr(), float(b1), float(b2), float(group['eps']),
-                                            flat.numel(), stream), 'nerf_adam_update')
+            _lib.check(lib.nerf_adam_update_ex(flat.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(), g.data_ptr(),
+                                               lr.data_ptr(), self.device_state.data_ptr(), float(b1), float(b2), float(group['eps']),
+                                               float(self.grad_mult), int(bound and self.zero_bound_grads), flat.numel(), stream),
+                       'nerf_adam_update_ex')
         return loss
 
     # ---- torch.optim.Adam-compatible checkpoints ------------------------------------------------------------

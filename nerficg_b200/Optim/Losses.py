@@ -52,6 +52,14 @@ class BaseLoss(torch.nn.Module):
         for item in self.loss_metrics + self.quality_metrics:
             item.reset()
 
+    def log_fused(self, total: float) -> None:
+        """Running average of the training loss when the step ran as one captured graph (K8 returns only the weighted
+        total, so it is booked on the first loss term; the per-term split needs the autograd path, TRAINING.FUSED_STEP=False)."""
+        if self.loss_metrics:
+            item = self.loss_metrics[0]
+            item._sum[0] += float(total)
+            item._n[0] += 1
+
     def forward(self, configurations: dict[str, dict[str, Any]]) -> torch.Tensor:
         try:
             if self.activate_logging:

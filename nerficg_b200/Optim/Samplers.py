@@ -35,26 +35,54 @@ class RandomSequentialSampler:
         return torch.stack(out)
 
 
+class SequentialSampler:
+    """0, 1, ..., n-1, 0, ... (Samplers/utils.py: the ``random=False`` view order)."""
+
+    def __init__(self, num_elements: int) -> None:
+        self.num_elements = num_elements
+        self.cursor = 0
+
+    def get(self, num_samples: int = 1) -> torch.Tensor:
+        out = (torch.arange(num_samples) + self.cursor) % self.num_elements
+        self.cursor = int((self.cursor + num_samples) % self.num_elements)
+        return out
+
+
+def _takes_pixel_ids(view) -> bool:
+    """Our View.get_rays(pixel_ids) generates only the sampled rays on the device (K0); the reference's
+    View.get_rays() (src/Datasets/utils.py:1053) takes no argument and returns the whole image's RayBatch."""
+    import inspect
+    try:
+        return len(inspect.signature(view.get_rays).parameters) >= 1
+    except (TypeError, ValueError):
+        return False
+
+
 class DatasetSampler:
-    """One random view per call, then random pixels of that view (DatasetSamplers.py:10-41)."""
+    """One view per call (random permutation or sequential), then pixels of that view (DatasetSamplers.py:10-41)."""
 
     def __init__(self, dataset, random: bool = True, img_sampler_cls=RandomImageSampler) -> None:
         self.mode = dataset.mode
-        self.id_sampler = RandomSequentialSampler(len(dataset))
-        self.img_samplers = [img_sampler_cls(v.camera.width * v.camera.height) for v in dataset]
+        self.id_sampler = RandomSequentialSampler(len(dataset)) if random else SequentialSampler(len(dataset))
+        self.img_samplers = [img_sampler_cls(v.camera.width * v.camera.height) for v in dataset] if img_sampler_cls else None
 
     def get(self, dataset, ray_batch_size: int | None = None) -> dict:
         if dataset.mode != self.mode:
             raise Framework.SamplerError(f'sampler initialised for mode "{self.mode}", dataset is in mode "{dataset.mode}"')
         sample_id = int(self.id_sampler.get(1).item())
         view = dataset[sample_id]
-        ray_ids = ray_batch = None
-        if ray_batch_size is not None:
-            ray_ids = self.img_samplers[sample_id].get(ray_batch_size).to(Framework.config.GLOBAL.DEFAULT_DEVICE)
+        image_sampler = ray_ids = ray_batch = None
+        if self.img_samplers and ray_batch_size is not None:
+            image_sampler = self.img_samplers[sample_id]
+            ray_ids = image_sampler.get(ray_batch_size).to(Framework.config.GLOBAL.DEFAULT_DEVICE)
             collection = dataset.ray_collection[self.mode]
-            ray_batch = collection[sample_id][ray_ids] if collection is not None else view.get_rays(ray_ids)   # K0: only the sampled pixels
-        return {'sample_id': sample_id, 'view': view, 'image_sampler': self.img_samplers[sample_id], 'ray_ids': ray_ids,
-                'ray_batch': ray_batch}
+            if collection is not None:
+                ray_batch = collection[sample_id][ray_ids]
+            elif _takes_pixel_ids(view):
+                ray_batch = view.get_rays(ray_ids)        # K0: only the sampled pixels
+            else:
+                ray_batch = view.get_rays()[ray_ids]      # a reference View: whole image, then index (DatasetSamplers.py:39)
+        return {'sample_id': sample_id, 'view': view, 'image_sampler': image_sampler, 'ray_ids': ray_ids, 'ray_batch': ray_batch}
 
 
 class RayPoolSampler:

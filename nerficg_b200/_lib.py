@@ -33,6 +33,7 @@ _PROTOTYPES = {
     'nerf_mlp_backward_wgrad': (c_int, [c_void_p] * 3 + [c_int, c_int, c_float, c_void_p]),
     'nerf_adam_tick': (c_int, [c_void_p, c_float, c_float, c_void_p]),
     'nerf_adam_update': (c_int, [c_void_p] * 6 + [c_float, c_float, c_float, c_int64, c_void_p]),
+    'nerf_adam_update_ex': (c_int, [c_void_p] * 6 + [c_float, c_float, c_float, c_float, c_int, c_int64, c_void_p]),
     'nerf_generate_rays': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(ctypes.c_double), c_int, c_int,
                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
     'nerf_gather_rays': (c_int, [c_void_p] * 11 + [c_int64, c_void_p]),

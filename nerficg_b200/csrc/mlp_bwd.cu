@@ -451,7 +451,10 @@ static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbs
   p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
   if (phases & 1) {
     NERF_CHECK_ARG(d_rgbsigma && rgbsigma && packed && params, "mlp_backward: null pointer");
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};  // the attribute is per device
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool& attr_set = attr_set_dev[dev__ & 63];
     if (!attr_set) {
       cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
       NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));

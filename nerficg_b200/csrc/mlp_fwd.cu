@@ -651,7 +651,10 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
   p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
   const int group_pairs = ((p.n_tiles + 1) / 2 + 1) / 2;  // one cluster iteration = 2 slots x 2 tiles
   const int grid = 2 * (group_pairs < kNumSMs / 2 ? group_pairs : kNumSMs / 2);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // the attribute is per device
+    int dev__ = 0;
+    cudaGetDevice(&dev__);
+    bool& attr_set = attr_set_dev[dev__ & 63];
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
     cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);

@@ -45,6 +45,14 @@ def allreduce_mean_(flat_grads: list[torch.Tensor]) -> None:
         g.mul_(1.0 / w)
 
 
+def allreduce_sum_(flat_grads: list[torch.Tensor]) -> None:
+    """In place SUM over ranks; the 1/world of the mean is folded into the optimiser's gradient read (K7 grad_mult)."""
+    if world_size() == 1:
+        return
+    for g in flat_grads:
+        td.all_reduce(g, op=td.ReduceOp.SUM)
+
+
 def broadcast_parameters_(flat_params: list[torch.Tensor], src: int = 0) -> None:
     """Makes every rank start from rank ``src``'s weights (ranks seeded differently for their ray batches)."""
     if world_size() == 1:

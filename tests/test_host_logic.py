@@ -28,11 +28,28 @@ def test_plugin_triple_and_registry(cfg):
     with pytest.raises(Framework.MethodError):
         Methods.import_method('InstantNGP')
 
+    class FakeFramework:            # stands for the reference's Framework module (the real one: tests/test_reference_dropin.py)
+        class Configurable: pass
+        class Directories: OUTPUT_DIR = NERFICG_ROOT = None
+        config = Framework.ConfigParameterList.fromDict({'GLOBAL': {'METHOD_TYPE': 'NeRF'}, 'RENDERER': {'N_SAMPLES': 48, 'COARSE_RATIO': 0.5},
+                                                         'TRAINING': {'WANDB': {'ACTIVATE': False}}})
+
     class FakeReference:            # stands for the reference's Implementations module
+        Framework = FakeFramework
         class Methods:
             modules = {}
+    from nerficg_b200.Implementations import uninstall_from_reference
     install_into_reference(FakeReference)
-    assert FakeReference.Methods.modules['NeRF'] is mod
+    try:
+        assert FakeReference.Methods.modules['NeRF'] is mod
+        assert Framework.config is FakeFramework.config and Framework.Directories is FakeFramework.Directories
+        FakeFramework.config = Framework.ConfigParameterList.fromDict({'GLOBAL': {}, 'RENDERER': {'N_SAMPLES': 12}})   # host rebinds its global
+        assert Framework.config.RENDERER.N_SAMPLES == 12
+        with pytest.raises(Framework.FrameworkError):
+            Framework.load_config(None)          # while bound, the configuration belongs to the host
+    finally:
+        uninstall_from_reference(FakeReference)
+    assert Framework.config is not FakeFramework.config
 
 
 def test_model_state_dict_matches_reference_layout(cfg):
