@@ -42,6 +42,8 @@ _PROTOTYPES = {
     'nerf_selftest_umma': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_umma2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nerf_selftest_tmem_read': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    'nerf_selftest_l2_stream': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_void_p]),
+    'nerf_selftest_l2_stream_lsu': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -249,14 +249,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       const int64_t e = (int64_t)tile * kTile + row;
       const bool valid = tile_ok && e < p.n_evals;
 
+      auto gstash_issue = [&](int region, uint32_t src, uint32_t bytes) {  // one thread, after the slot's warps fenced + met
+        if (tg == 0 && tile_ok) {
+          #if defined(NERF_EXP_STORE_WRAP)   // diagnostic: every image lands in a 16-tile window that stays in L2 (results are wrong downstream)
+          const uint64_t tile_w = (uint64_t)(tile & 15);
+#else
+          const uint64_t tile_w = (uint64_t)tile;
+#endif
+          uint8_t* dst = p.gstash + grad_region_offset(region, n_tiles64) + tile_w * grad_region_tile_bytes(region);
+#if defined(NERF_EXP_NOSTORE)
+          (void)dst;
+#elif defined(NERF_EXP_SPLIT_STORE)
+          for (uint32_t off = 0; off < bytes; off += kPanelBytes128) bulk_s2g_hint(dst + off, src + off, kPanelBytes128, l2_evict_first());
+#elif defined(NERF_EXP_NOHINT)
+          bulk_s2g(dst, src, bytes);
+#else
+          bulk_s2g_hint(dst, src, bytes, l2_evict_first());
+#endif
+          bulk_commit();
+        }
+      };
       auto gstash_store = [&](int region, uint32_t src, uint32_t bytes) {
         fence_proxy_async_smem();
         named_bar_sync(bar_id, kEpiThreadsPerSlot);
-        if (tg == 0 && tile_ok) {
-          bulk_s2g_hint(p.gstash + grad_region_offset(region, n_tiles64) + (uint64_t)tile * grad_region_tile_bytes(region), src, bytes,
-                        l2_evict_first());
-          bulk_commit();
-        }
+        gstash_issue(region, src, bytes);
       };
       auto gstash_drain = [&]() {
         const long long t0 = prof ? clock64() : 0;
@@ -393,6 +409,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           }
         };
         if (st == 1) run(BoolTag<true>{}); else run(BoolTag<false>{});
+#if defined(NERF_EXP_EARLY_HANDOFF)
+        fence_proxy_async_smem();
+        tc_fence_before();
+        if (st < kBwdStages - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+        }
+        named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        gstash_issue(kGradF + st, act, kActBytes);
+#else
         gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
         if (st < kBwdStages - 1) {
           fence_proxy_async_smem();
@@ -402,6 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         } else {
           tc_fence_before();  // accumulator drained; released by the next tile's prologue arrive
         }
+#endif
       }
     }
     if (tg == 0) bulk_wait_all<0>();

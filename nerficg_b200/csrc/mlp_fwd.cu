@@ -374,15 +374,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       const int ray = valid ? (int)(e / p.n_samples) : 0;
 
       // stash helper: one thread bulk-stores an image from shared memory after the slot's warps fenced their writes
+      auto stash_issue = [&](int region, uint32_t src, uint32_t bytes) {  // one thread, after the slot's warps fenced + met
+        if (tg == 0 && tile_ok) {
+          #if defined(NERF_EXP_STORE_WRAP)   // diagnostic: every image lands in a 16-tile window that stays in L2 (results are wrong downstream)
+          const uint64_t tile_w = (uint64_t)(tile & 15);
+#else
+          const uint64_t tile_w = (uint64_t)tile;
+#endif
+          uint8_t* dst = p.stash + stash_region_offset(region, n_tiles64) + tile_w * stash_region_tile_bytes(region);
+#if defined(NERF_EXP_NOSTORE)
+          (void)dst;
+#elif defined(NERF_EXP_SPLIT_STORE)
+          for (uint32_t off = 0; off < bytes; off += kPanelBytes128) bulk_s2g_hint(dst + off, src + off, kPanelBytes128, l2_evict_first());
+#elif defined(NERF_EXP_NOHINT)
+          bulk_s2g(dst, src, bytes);
+#else
+          bulk_s2g_hint(dst, src, bytes, l2_evict_first());
+#endif
+          bulk_commit();
+        }
+      };
       auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {
         if (kTrain) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, kEpiThreadsPerSlot);
-          if (tg == 0 && tile_ok) {
-            bulk_s2g_hint(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region), src, bytes,
-                          l2_evict_first());
-            bulk_commit();
-          }
+          stash_issue(region, src, bytes);
         }
       };
       // before overwriting a buffer that may still be read by an in-flight bulk store
@@ -510,6 +526,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           write_half_row(enc, row, half, vals);
           stash_store(kStashDir, enc, kPanelBytes128);
         }
+#if defined(NERF_EXP_EARLY_HANDOFF)
+        // operands are handed to the MMA issuer per warp BEFORE the slot's warps meet for the image store / bias refill
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+        named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        if (kTrain) stash_issue(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
+        if (tg == 0) bias_fetch(st + 1);
+#else
         stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);  // (training) fence + slot barrier + bulk store
         fence_proxy_async_smem();
         if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);  // every warp of the slot is done with this stage's bias
@@ -517,6 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         tc_fence_before();
         __syncwarp();  // one (possibly remote) arrival per warp
         if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+#endif
         // ReLU bits -> stash, after the hand-off: a plain global store can stall its warp under the stash's HBM write load
         if (kTrain && relu && tile_ok) {
           uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +

@@ -256,3 +256,138 @@ extern "C" int nerf_selftest_tmem_read(unsigned long long* out, int n_warps, int
   NERF_CHECK_LAUNCH("tmem_read_probe_kernel");
   return 0;
 }
+
+// ---- L2 -> SM streaming probe (development aid) -----------------------------------------------------------------
+// Every CTA streams `iters` chunks of 16 KB from an L2-resident window into an 8-stage shared-memory ring with 1-D bulk
+// copies (mode bit 0) and/or bulk-stores 16 KB chunks back into the window (mode bit 1); out[0] = cycles of the slowest
+// CTA, out[1] = bytes moved per CTA.  Answers: how many bytes per cycle and SM does the L2 deliver to 148 TMA engines?
+namespace nerf {
+__global__ void __launch_bounds__(64, 1) l2_stream_kernel(unsigned long long* out, uint8_t* window, uint32_t window_bytes, int mode, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int kStages = 8;
+  constexpr uint32_t kChunk = 16384;
+  const uint32_t bars = smem_base + kStages * kChunk;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) tc::mbar_init(bars + 8 * i, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const uint32_t n_chunks = window_bytes / kChunk;
+  uint32_t c = (blockIdx.x * 977u) % n_chunks;
+  const long long t0 = clock64();
+  uint32_t phase = 0;
+  int stage = 0;
+  for (int i = 0; i < iters; ++i) {
+    if (i >= kStages && (mode & 1)) tc::mbar_wait(bars + 8 * stage, phase ^ 1);   // the load that used this stage has landed
+    if (mode & 2) {
+      if (i >= kStages) tc::bulk_wait_read<kStages - 1>();
+      tc::bulk_s2g(window + (uint64_t)c * kChunk, smem_base + stage * kChunk, kChunk);
+      tc::bulk_commit();
+    }
+    if (mode & 1) {
+      tc::mbar_arrive_expect_tx(bars + 8 * stage, kChunk);
+      tc::bulk_g2s(smem_base + stage * kChunk, window + (uint64_t)((c + n_chunks / 2) % n_chunks) * kChunk, kChunk, bars + 8 * stage);
+    }
+    c = (c + 148u) % n_chunks;
+    if (++stage == kStages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+  if (mode & 1)
+    for (int i = 0; i < kStages && i < iters; ++i) {   // drain
+      int sidx = (stage + i) % kStages;
+      uint32_t ph = (sidx >= stage) ? (phase ^ 1) : phase;
+      tc::mbar_wait(bars + 8 * sidx, ph);
+    }
+  if (mode & 2) tc::bulk_wait_all<0>();
+  const unsigned long long dt = (unsigned long long)(clock64() - t0);
+  atomicMax(out, dt);
+  if (blockIdx.x == 0) out[1] = (unsigned long long)iters * kChunk * (((mode & 1) ? 1 : 0) + ((mode & 2) ? 1 : 0));
+}
+}  // namespace nerf
+
+// LSU flavour of the probe: `n_warps` warps copy 16 KB chunks between the window and shared memory with 16-byte
+// ld.shared + st.global (mode bit 2, "stores") and/or ld.global + st.shared (mode bit 3, "loads"), optionally while thread 0
+// keeps the TMA ring of bulk LOADS busy (mode bit 0) -- can the LSU path carry the stash stores next to the weight ring?
+namespace nerf {
+__global__ void __launch_bounds__(288, 1) l2_stream_lsu_kernel(unsigned long long* out, uint8_t* window, uint32_t window_bytes, int mode, int iters,
+                                                              int n_warps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  constexpr int kStages = 8;
+  constexpr uint32_t kChunk = 16384;
+  const uint32_t bars = smem_base + kStages * kChunk;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) tc::mbar_init(bars + 8 * i, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const uint32_t n_chunks = window_bytes / kChunk;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t0 = clock64();
+  if (warp == 0) {
+    if (lane == 0 && (mode & 1)) {   // TMA load ring
+      uint32_t c = (blockIdx.x * 977u) % n_chunks, phase = 0;
+      int stage = 0;
+      for (int i = 0; i < iters; ++i) {
+        if (i >= kStages) tc::mbar_wait(bars + 8 * stage, phase ^ 1);
+        tc::mbar_arrive_expect_tx(bars + 8 * stage, kChunk);
+        tc::bulk_g2s(smem_base + stage * kChunk, window + (uint64_t)c * kChunk, kChunk, bars + 8 * stage);
+        c = (c + 148u) % n_chunks;
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      for (int i = 0; i < kStages && i < iters; ++i) {
+        int sidx = (stage + i) % kStages;
+        tc::mbar_wait(bars + 8 * sidx, (sidx >= stage) ? (phase ^ 1) : phase);
+      }
+    }
+  } else if (warp - 1 < n_warps) {
+    // each LSU warp moves its share of every chunk: 16 B per lane per instruction, fully coalesced (512 B per warp instruction)
+    const int w = warp - 1;
+    uint32_t c = (blockIdx.x * 977u + 31u) % n_chunks;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < iters; ++i) {
+      uint4* g = reinterpret_cast<uint4*>(window + (uint64_t)c * kChunk);
+      uint4* sp = reinterpret_cast<uint4*>(smem_gen + (i % kStages) * kChunk);
+      for (int q = w * 32 + lane; q < (int)(kChunk / 16); q += n_warps * 32) {
+        if (mode & 4) g[q] = sp[q];
+        if (mode & 8) { uint4 v = __ldcg(g + q); acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+      }
+      c = (c + 148u) % n_chunks;
+    }
+    if (acc.x == 0x12345678u && acc.y == 1u) out[2] = acc.z;   // keep the loads alive
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicMax(out, (unsigned long long)(clock64() - t0));
+    if (blockIdx.x == 0) out[1] = (unsigned long long)iters * kChunk * (((mode & 1) ? 1 : 0) + ((mode & 4) ? 1 : 0) + ((mode & 8) ? 1 : 0));
+  }
+}
+}  // namespace nerf
+
+extern "C" int nerf_selftest_l2_stream_lsu(unsigned long long* out, void* window, uint32_t window_bytes, int mode, int iters, int n_ctas,
+                                           int n_warps, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(out && window && window_bytes >= (1u << 20) && iters > 0 && n_ctas > 0 && n_warps >= 1 && n_warps <= 8, "selftest_l2_stream_lsu: bad arguments");
+  const int smem = 8 * 16384 + 256 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(l2_stream_lsu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  NERF_CHECK_ARG(e == cudaSuccess, "selftest_l2_stream_lsu: %s", cudaGetErrorString(e));
+  l2_stream_lsu_kernel<<<n_ctas, 288, smem, static_cast<cudaStream_t>(stream)>>>(out, static_cast<uint8_t*>(window), window_bytes, mode, iters, n_warps);
+  NERF_CHECK_LAUNCH("l2_stream_lsu_kernel");
+  return 0;
+}
+
+extern "C" int nerf_selftest_l2_stream(unsigned long long* out, void* window, uint32_t window_bytes, int mode, int iters, int n_ctas, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(out && window && window_bytes >= (1u << 20) && iters > 0 && n_ctas > 0, "selftest_l2_stream: bad arguments");
+  const int smem = 8 * 16384 + 256 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(l2_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  NERF_CHECK_ARG(e == cudaSuccess, "selftest_l2_stream: %s", cudaGetErrorString(e));
+  l2_stream_kernel<<<n_ctas, 64, smem, static_cast<cudaStream_t>(stream)>>>(out, static_cast<uint8_t*>(window), window_bytes, mode, iters);
+  NERF_CHECK_LAUNCH("l2_stream_kernel");
+  return 0;
+}

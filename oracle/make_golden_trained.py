@@ -1,6 +1,6 @@
 """Trained-regime golden vectors from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY; build container only.
 
-    python oracle/make_golden_trained.py [--steps 400] [--batch 512]
+    python oracle/make_golden_trained.py [--steps 900] [--batch 512]
 
 Every other golden in tests/golden/ uses freshly initialised weights (sigma ~ 0, rgb ~ 0.5), where fp16 operand
 rounding is harmless.  This script trains the reference's own NeRF (its Model / Renderer / NeRFLoss / Adam x LambdaLR,
@@ -45,9 +45,10 @@ def camera_rays(theta: float, phi: float, width: int):
 
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--steps', type=int, default=900)
     ap.add_argument('--batch', type=int, default=512)
     ap.add_argument('--width', type=int, default=100)
+    ap.add_argument('--lr-steps', type=int, default=500000, help='max_steps of the LR policy (the shipped 500k keeps lr ~ 5e-4 over a short run)')
     args = ap.parse_args()
 
     ref = load_reference(n_samples=192, coarse_ratio=0.3333333, seed=0)
@@ -74,8 +75,7 @@ def main() -> None:
     renderer = method.RENDERER(model)
     assert (renderer.n_samples_coarse_nerf, renderer.n_samples_nerf) == (64, 128)
     optimizer = torch.optim.Adam(model.parameters(), lr=1.0)
-    # the schedule of a short run: the reference's policy with max_steps = the run length
-    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=LRDecayPolicy(lr_init=5e-4, lr_final=5e-5, max_steps=args.steps))
+    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=LRDecayPolicy(lr_init=5e-4, lr_final=5e-5, max_steps=args.lr_steps))
     loss_fn = NeRFLoss(1.0, 0.0, True)
     t0 = time.time()
     for it in range(args.steps):

@@ -153,3 +153,25 @@ def test_postprocess_outputs_shapes_and_depth_coloring(cfg, golden):
     assert torch.equal(out['rgb'], rgb.clamp(0, 1))
     assert (out['depth'] - g['spectral_masked']).abs().max() <= 1e-6
     assert (out['depth_coarse'] - g['spectral_masked']).abs().max() <= 1e-6
+
+
+def test_ssim_matches_an_independent_implementation():
+    """SSIM of the test-set metrics (reference Base/Renderer.py:130-133, torchmetrics defaults restated): identical images
+    give 1, the measure is symmetric, and it equals a scipy Gaussian-filter implementation on the un-padded interior."""
+    import numpy as np
+    from scipy.ndimage import correlate
+    from nerficg_b200.Methods.Base.Renderer import psnr_8bit, ssim
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(3, 40, 50, generator=g)
+    b = (a + 0.1 * torch.randn(3, 40, 50, generator=g)).clamp(0, 1)
+    assert ssim(a, a) == pytest.approx(1.0, abs=1e-6) and ssim(a, b) == pytest.approx(ssim(b, a), abs=1e-7)
+    x = np.arange(11) - 5
+    g1 = np.exp(-(x / 1.5) ** 2 / 2)
+    k = np.outer(g1 / g1.sum(), g1 / g1.sum())
+    f = lambda img: np.stack([correlate(c, k, mode='mirror') for c in img])
+    A, B = a.numpy().astype(np.float64), b.numpy().astype(np.float64)
+    mu_a, mu_b = f(A), f(B)
+    va, vb, cab = f(A * A) - mu_a ** 2, f(B * B) - mu_b ** 2, f(A * B) - mu_a * mu_b
+    m = ((2 * mu_a * mu_b + 1e-4) * (2 * cab + 9e-4)) / ((mu_a ** 2 + mu_b ** 2 + 1e-4) * (va + vb + 9e-4))
+    assert ssim(a, b) == pytest.approx(m[:, 5:-5, 5:-5].mean(), abs=1e-5)
+    assert psnr_8bit(a, a) > 100.0

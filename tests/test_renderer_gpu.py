@@ -88,12 +88,23 @@ def test_loss_and_gradients_golden(fw, golden):
     loss = NeRFLoss(1.0, 0.0, True)(out, rays, g['bg'].to(DEV))
     assert abs(loss.item() - g['loss'].item()) <= 1e-3 * g['loss'].item()
     loss.backward()
-    worst = 0.0
+    worst, worst_head, heads = 0.0, 0.0, {}
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        rel = abs(p.grad.norm().item() - g['grad_norm'][k].item()) / (g['grad_norm'][k].item() + 1e-12)
-        worst = max(worst, rel)
+        ref_n, ref_h = g['grad_norm'][k].item(), g['grad_head'][k]
+        worst = max(worst, abs(p.grad.norm().item() - ref_n) / (ref_n + 1e-12))
+        # the reference's first 48 gradient ELEMENTS of every tensor (relative L2; 1- and 3-element biases are sums that
+        # cancel, so they are measured against the size of the whole tensor like in test_mlp_gpu)
+        got_h = p.grad.flatten()[:ref_h.numel()].cpu()
+        heads[k] = float((got_h - ref_h).norm() / (max(ref_h.norm().item(), 0.05 * ref_n) + 1e-30))
+        worst_head = max(worst_head, heads[k])
+    import json, os
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_measured.jsonl', 'a') as f:
+        f.write(json.dumps({'test': 'loss_and_gradients_golden', 'worst_norm': worst, 'worst_head': worst_head,
+                            'rel_head': {k: round(v, 4) for k, v in heads.items()}}) + '\n')
     assert worst <= 1e-1, worst   # stated tolerance vs the fp32 reference (ReLU-mask flips, see test_mlp_gpu)
+    assert worst_head <= 1e-1, heads
 
 
 def test_state_dict_roundtrip_and_single_pass(fw, tmp_path):
@@ -160,7 +171,7 @@ def test_fused_step_matches_autograd_step(fw):
                 trainer.fused_step(batch, ds.default_camera, use_graph=(mode == 'fused-graph'))
         torch.cuda.synchronize()
         if mode == 'fused-graph':
-            assert trainer._fused[len(batch)].graph is not None
+            assert next(iter(trainer._fused.values())).graph is not None
         results.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
     # Adam turns gradients into +-lr steps, so last-bit differences of near-zero gradients (fp32 atomics order)
     # may move single weights by a fraction of lr; anything systematic would move all of them by 4 * lr = 2e-3

@@ -36,6 +36,22 @@ def test_umma_cta_pair_selftest(ops, n, k):
     assert torch.allclose(out.double(), ref, rtol=1e-4, atol=1e-3), (out.double() - ref).abs().max()
 
 
+# K2 vs the CPU oracle.  SURVEY 8c allows a 1e-5 fraction of outliers "at the denom < 1e-5 branch", but that branch is not the
+# only place where the reference's arithmetic is ill-conditioned: a sample that falls into a near-empty bin (pdf ~ 1e-5 / sum)
+# inherits the cdf's rounding error times 1/pdf * bin width, i.e. ONE ulp of the cdf (6e-8) moves it by ~4e-4, and torch's own
+# CPU and CUDA cumsum/sum differ by ulps.  What IS exact is the inverse-CDF property |F(z) - u| <= 2e-5 under the oracle's own
+# cdf (asserted for EVERY sample below).  The bound here is the measured outlier fraction (gpurun_out/parity_measured.jsonl,
+# DESIGN.md section 2) with a 2x margin; test inputs (weights = rand^8) are chosen to stress near-empty bins.
+K2_OUTLIER_FRACTION = 5e-3    # measured on B200 (round 2): 2.7e-4 .. 2.6e-3 over these cases, max |dz| 5e-2 at the `denom < 1e-5` branch
+
+
+def _record_k2(name, frac, worst, numel):
+    import json, os
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_measured.jsonl', 'a') as f:
+        f.write(json.dumps({'test': 'K2_' + name, 'outlier_fraction_gt_2e-5': frac, 'max_abs': worst, 'samples': numel}) + '\n')
+
+
 def test_stratified_golden(ops, golden):
     g = golden('stratified')
     z = ops.sample_stratified(g['n'], g['nc'], g['near'], g['far'], g['u'].to(DEV), torch.device(DEV)).cpu()
@@ -61,7 +77,8 @@ def test_importance_golden(ops, golden):
     def check_close(a, b):
         err = (a - b).abs()
         frac, worst = (err > 2e-5).float().mean().item(), err.max().item()
-        assert frac <= 1e-2 and worst <= 0.1, (frac, worst)
+        _record_k2('importance_golden', frac, worst, err.numel())
+        assert frac <= K2_OUTLIER_FRACTION and worst <= 0.1, (frac, worst)
     check_close(fine.cpu(), g['zf_rand'])
     check_close(merged.cpu(), g['merged_rand'])
     merged, fine = ops.sample_importance(g['z_coarse'].to(DEV), g['w_coarse'].to(DEV), g['nf'], None, True)
@@ -81,7 +98,8 @@ def test_importance_oracle(ops, n, nc, nf):
     # samples in near-empty bins amplify cdf rounding by 1/pdf and the `denom < 1e-5` branch is a
     # discontinuity (SURVEY hard part 7): positions agree to 2e-5 except for a small fraction of outliers,
     # and EVERY sample satisfies the inverse-CDF property |F(z) - u| <= 2e-5 under the oracle's own CDF
-    assert (err > 2e-5).float().mean() <= 1e-2, err.max()
+    _record_k2(f'importance_oracle[{n},{nc},{nf}]', (err > 2e-5).float().mean().item(), err.max().item(), err.numel())
+    assert (err > 2e-5).float().mean() <= K2_OUTLIER_FRACTION, err.max()
     edges = 0.5 * (zc[:, :-1] + zc[:, 1:]).double()
     v = w[:, 1:-1].double() + 1e-5
     cdf = torch.cat((torch.zeros(n, 1, dtype=torch.double), torch.cumsum(v / v.sum(-1, keepdim=True), -1)), -1)
