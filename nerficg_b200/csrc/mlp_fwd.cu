@@ -184,6 +184,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
   const uint32_t bar_acc_ready = bar_a_ready + 16;        // [2] accumulator complete (multicast commit)
   const uint32_t bar_bias = bar_acc_ready + 16;           // [2] the slot's bias vector of the next stage has landed
   const uint32_t tmem_slot = bar_bias + 16;               // uint32: TMEM base address
+  const uint32_t bar_img_full = tmem_slot + 16;           // [2] (LSU-store experiment) the slot's stash image is complete in shared memory
+  const uint32_t bar_img_empty = bar_img_full + 16;       // [2] ... and has been copied out by the slot's store warp
   const uint32_t rank = cluster_ctarank();                // 0 = leader
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,6 +199,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
       mbar_init(bar_acc_ready + 8 * s, 1);
       mbar_init(bar_bias + 8 * s, 1);
+      mbar_init(bar_img_full + 8 * s, 8);   // one arrival per epilogue warp of the slot
+      mbar_init(bar_img_empty + 8 * s, 1);
     }
     fence_barrier_init();
   }
@@ -304,7 +308,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 9, 1ull);
       }
+#if defined(NERF_EXP_LSU_STORE)
+    } else if (warp >= 2) {
+      // =============================== stash store warps (one per slot) ===============================
+      // Measured (tools/l2_probe.py): one SM's TMA engine moves 66 B/clk of bulk loads but only 27-32 B/clk of bulk stores,
+      // and a queued 64 KB image store delays the weight-ring loads behind it (the issuer's W-full wait tripled in training).
+      // Here the images leave through the LSU instead: a linear 16-byte copy shared -> global (the stash image IS the
+      // shared-memory image), one warp per slot, so the TMA engine only carries the weight ring.
+      if (kTrain) {
+        const int slot = warp - 2;
+        const uint32_t act = smem_base + slot * kSlotBytes;
+        const uint8_t* act_g = smem_raw + slot * kSlotBytes;
+        const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+        uint32_t ph = 0;
+        (void)act;
+        auto copy_out = [&](int region, const uint8_t* src, uint32_t bytes, int tile) {
+          uint4* dst = reinterpret_cast<uint4*>(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region));
+          const uint4* sp = reinterpret_cast<const uint4*>(src);
+          const int n16 = (int)(bytes >> 4);
+#pragma unroll 2
+          for (int q = lane; q < n16; q += 64) {
+            const uint4 v0 = sp[q], v1 = sp[q + 32];
+            __stcs(dst + q, v0);
+            __stcs(dst + q + 32, v1);
+          }
+        };
+        for (int it = 0; it < n_iters; ++it) {
+          if (!active(it, slot)) break;
+          const int tile = group_of(it, slot) * 2 + (int)rank;
+          const bool tile_ok = tile < p.n_tiles;
+          for (int ev = 0; ev < 11; ++ev) {   // ENC | H0..H7 | DIR + F | G  (the epilogue's event sequence)
+            mbar_wait(bar_img_full + 8 * slot, ph);
+            if (tile_ok) {
+              if (ev == 0) copy_out(kStashEnc, act_g + kActBytes, kPanelBytes128, tile);
+              else if (ev <= 8) copy_out(kStashH0 + ev - 1, act_g, kActBytes, tile);
+              else if (ev == 9) {
+                copy_out(kStashDir, act_g + kActBytes, kPanelBytes128, tile);
+                copy_out(kStashF, act_g, kActBytes, tile);
+              } else copy_out(kStashG, act_g, 2 * kPanelBytes128, tile);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_img_empty + 8 * slot);
+            ph ^= 1;
+          }
+        }
+      }
     } else if (warp == 1) {
+#else
+    } else if (warp == 1) {
+#endif
       // =============================== relay (peer CTA) ===============================
       // tells the leader's issuer that this CTA's half of ring stage s has landed (bulk copies can only signal a
       // barrier of their own CTA, and mbarriers cannot be waited on remotely)
@@ -346,6 +398,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
     const uint32_t t_acc = t_slot + 128 * half;                            // hidden stages: columns [128 * half, +128)
     const uint32_t act_h = act + 2 * half * kPanelBytes128 + row_off;      // this row in the first of this half's two panels
     uint32_t acc_phase = 0, bias_phase = 0;
+    uint32_t img_events = 0, img_drained = 0;   // (LSU-store experiment) stash images handed to / finished by the slot's store warp
+    (void)img_events;
+    (void)img_drained;
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);  // both CTAs announce their operands to the leader
     const bool prof = prof_on && tg == 0 && slot == 0;
@@ -394,6 +449,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           bulk_commit();
         }
       };
+#if defined(NERF_EXP_LSU_STORE)
+      auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {   // event: this warp's part of the image is in shared memory
+        if (kTrain && region != kStashDir) {                                 // (DIR leaves together with F: one event)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_img_full + 8 * slot);
+          ++img_events;
+        }
+      };
+#else
       auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {
         if (kTrain) {
           fence_proxy_async_smem();
@@ -401,7 +465,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           stash_issue(region, src, bytes);
         }
       };
+#endif
       // before overwriting a buffer that may still be read by an in-flight bulk store
+#if defined(NERF_EXP_LSU_STORE)
+      auto stash_drain = [&]() {   // every event issued so far has been copied out (at most one is outstanding)
+        if (kTrain && img_events != img_drained) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(bar_img_empty + 8 * slot, (img_events - 1) & 1u);
+          img_drained = img_events;
+          if (prof) t_drain += clock64() - t0;
+        }
+      };
+#else
       auto stash_drain = [&]() {
         if (kTrain) {
           const long long t0 = prof ? clock64() : 0;
@@ -410,6 +485,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           if (prof) t_drain += clock64() - t0;
         }
       };
+#endif
 
       // ---------------- prologue: position encoding -> enc panel (each half writes its 32 of the 64 columns) ----------------
       // columns: [x y z | enc(x) 3..22 | enc(y) 23..42 | enc(z) 43..62 | 0]; half 0 needs enc(x) and the first nine
@@ -538,7 +614,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
 #else
         stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);  // (training) fence + slot barrier + bulk store
         fence_proxy_async_smem();
+#if defined(NERF_EXP_LSU_STORE)
+        named_bar_sync(bar_id, kEpiThreadsPerSlot);               // (the event hand-off above has no slot barrier of its own)
+#else
         if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);  // every warp of the slot is done with this stage's bias
+#endif
         if (tg == 0) bias_fetch(st + 1);
         tc_fence_before();
         __syncwarp();  // one (possibly remote) arrival per warp
@@ -604,6 +684,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         const uint32_t xch = act + 3 * kPanelBytes128 + (uint32_t)row * 16u;
         if (half == 1) st_shared_v4(xch, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(dens));
         stash_store(kStashG, act, 2 * kPanelBytes128);  // (training) its barrier also orders the exchange
+#if defined(NERF_EXP_LSU_STORE)
+        if (kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);
+#endif
         if (!kTrain) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, kEpiThreadsPerSlot);

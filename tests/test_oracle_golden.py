@@ -101,3 +101,27 @@ def test_camera_rays(golden):
         assert (d - case['direction']).abs().max() <= 1e-6
         assert (v - case['view_direction']).abs().max() <= 1e-6
         assert (v.norm(dim=-1) - 1).abs().max() <= 1e-6
+
+
+def test_oracle_matches_reference_in_the_trained_regime(golden):
+    """The oracle replayed at weights the REFERENCE trained itself (its own checkpoint file, held-out PSNR > 20 dB, sigma_max ~ 40):
+    deterministic render_rays, the randomised pass with the reference's noise, the loss and the leading gradient elements."""
+    import torch
+    from pathlib import Path
+    from oracle import nerf_oracle as O
+    g = golden('trained_render')
+    ckpt = torch.load(Path(__file__).resolve().parent / 'golden' / 'ref_trained_checkpoint.pt', map_location='cpu', weights_only=False)
+    sd = ckpt['model_state_dict']
+    assert g['psnr_heldout'] > 20.0 and g['sigma_max'] > 20.0 and ckpt['num_iterations_trained'] == g['steps']
+    out = O.render_rays(sd, g['o'], g['d'], g['v'], 2.0, 6.0, g['bg'], 64, 128)
+    for k, ref in g['out_det'].items():
+        assert (out[k] - ref).abs().max() <= 2e-5, k
+    assert (out['z'] - g['z']).abs().max() <= 1e-5
+    leaf = {k: v.clone().requires_grad_('frequency' not in k) for k, v in sd.items()}
+    out = O.render_rays(leaf, g['o'], g['d'], g['v'], 2.0, 6.0, g['bg'], 64, 128, g['draws'][0]['u_c'], g['draws'][0]['u_f'])
+    loss = O.nerf_loss(out, g['rgb_gt'], g['alpha_gt'], g['bg'])
+    assert abs(float(loss) - float(g['loss'])) <= 1e-5 * float(g['loss'])
+    loss.backward()
+    for k, ref in g['grad_head'].items():
+        got = leaf[k].grad.flatten()[:ref.numel()]
+        assert (got - ref).norm() <= 1e-3 * max(float(ref.norm()), 0.05 * float(g['grad_norm'][k])) + 1e-12, k

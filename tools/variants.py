@@ -15,6 +15,7 @@ VARIANTS = {
     'split': ('NERF_EXP_SPLIT_STORE',),          # 4 x 16 KB stores instead of one 64 KB store
     'nohint': ('NERF_EXP_NOHINT',),              # stores without the L2 evict_first policy
     'earlysplit': ('NERF_EXP_EARLY_HANDOFF', 'NERF_EXP_SPLIT_STORE'),
+    'lsu': ('NERF_EXP_LSU_STORE',),              # forward stash images leave through LSU store warps instead of TMA bulk stores
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
