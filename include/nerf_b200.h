@@ -104,7 +104,16 @@ int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsig
                       const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
                       void* stream);
 
-/* The two phases of nerf_mlp_backward, separately launchable (profiling, overlap with NCCL):
+/* nerf_mlp_backward runs the fused, layer-stationary pipeline (csrc/mlp_bwd_pipe.cu: data and weight gradients in one kernel, the
+ * per-layer output gradients never leave the chip) followed by a small residual weight-gradient kernel.  The same entry point is
+ * exported under its own name, and the previous two-kernel path (tile-major dgrad chain + layer-major wgrad) as *_legacy. */
+int nerf_mlp_backward_pipe(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                           const void* packed, const float* params, int n_rays, int n_samples, float grad_scale, void* stream);
+int nerf_mlp_backward_legacy(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
+                             const void* packed, const float* params, int n_rays, int n_samples, float grad_scale, void* stream);
+size_t nerf_mlp_backward_pipe_workspace_bytes(void);
+
+/* The two phases of the legacy path, separately launchable (profiling):
  * dgrad walks the chain backwards per tile and fills `workspace` with the per-layer output gradients;
  * wgrad reduces activations x gradients over all samples into `grads` (layer-major, HBM-bound). */
 int nerf_mlp_backward_dgrad(const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
@@ -160,6 +169,8 @@ int nerf_gather_rays(float* origin_dst, float* direction_dst, float* view_direct
 int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream);
 /* CTA-pair flavour (cta_group::2, one 2-CTA cluster): D[256][n] = A[256][k] * B[n][k]^T, K-major fp16. */
 int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream);
+/* ... with both operands stored reduction-major and read as MN-major (the pair flavour of the weight-gradient MMAs); n % 128 == 0. */
+int nerf_selftest_umma2_mn(float* d_out, const float* a, const float* b, int n, int k, void* stream);
 /* TMEM read-bandwidth probe (development aid): n_warps warps of one CTA issue `iters` accumulator loads each
  * (mode 0: 32x32b.x32, 1: two x32 in flight, 2: x16); out[0] = cycles, out[1] = bytes read from TMEM. */
 int nerf_selftest_tmem_read(unsigned long long* out, int n_warps, int mode, int iters, void* stream);

@@ -29,6 +29,9 @@ _PROTOTYPES = {
     'nerf_mlp_forward': (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p]),
     'nerf_mlp_backward_workspace_bytes': (c_size_t, [c_int64]),
     'nerf_mlp_backward': (c_int, [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p]),
+    'nerf_mlp_backward_pipe': (c_int, [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p]),
+    'nerf_mlp_backward_legacy': (c_int, [c_void_p] * 7 + [c_int, c_int, c_float, c_void_p]),
+    'nerf_mlp_backward_pipe_workspace_bytes': (c_size_t, []),
     'nerf_mlp_backward_dgrad': (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
     'nerf_mlp_backward_wgrad': (c_int, [c_void_p] * 3 + [c_int, c_int, c_float, c_void_p]),
     'nerf_adam_tick': (c_int, [c_void_p, c_float, c_float, c_void_p]),
@@ -41,6 +44,7 @@ _PROTOTYPES = {
     'nerf_debug_set_timing': (c_int, [c_void_p]),
     'nerf_selftest_umma': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_umma2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'nerf_selftest_umma2_mn': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nerf_selftest_tmem_read': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_l2_stream': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_l2_stream_lsu': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_int, c_void_p]),

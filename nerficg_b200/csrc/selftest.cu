@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(float* __restrict__ ou
 // CTA r of the 2-CTA cluster holds A rows [128r, 128r+128) and B rows [n/2 * r, n/2 * (r+1)); the leader issues
 // M = 256 MMAs, the peer announces its operands with a remote mbarrier arrive (the relay used by the MLP kernels)
 // and both CTAs are released by ONE multicast tcgen05.commit.  Checks the M / N split conventions of tc.cuh.
+// kMn: both operands are stored reduction-major (rows = k index, 64-wide column groups = M / N index, group stride k * 128 bytes)
+// and read as MN-major operands -- the cta_group::2 flavour of the weight-gradient MMAs (dW += dY^T X over the samples).
+template <bool kMn>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     selftest2_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int n, int k) {
   extern __shared__ uint8_t smem_raw[];
@@ -134,11 +137,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   const uint32_t tmem = tmem_base_s;
   for (int i = tid; i < 128 * k; i += 128) {
     int r = i / k, c = i % k;
-    *reinterpret_cast<uint16_t*>(sa + (c / 64) * (128 * 128) + panel_offset(r, c % 64)) = to_bits(a[(size_t)(128 * rank + r) * k + c], false);
+    uint8_t* dst = kMn ? sa + (r / 64) * (k * 128) + panel_offset(c, r % 64) : sa + (c / 64) * (128 * 128) + panel_offset(r, c % 64);
+    *reinterpret_cast<uint16_t*>(dst) = to_bits(a[(size_t)(128 * rank + r) * k + c], false);
   }
   for (int i = tid; i < nh * k; i += 128) {
     int r = i / k, c = i % k;
-    *reinterpret_cast<uint16_t*>(sb + (c / 64) * (nh * 128) + panel_offset(r, c % 64)) = to_bits(b[(size_t)(nh * rank + r) * k + c], false);
+    uint8_t* dst = kMn ? sb + (r / 64) * (k * 128) + panel_offset(c, r % 64) : sb + (c / 64) * (nh * 128) + panel_offset(r, c % 64);
+    *reinterpret_cast<uint16_t*>(dst) = to_bits(b[(size_t)(nh * rank + r) * k + c], false);
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -147,10 +152,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     mbar_wait_cluster(smem_u32(&bar_peer), 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(256, n, kF16, kF16, 0, 0);
-      for (int ks = 0; ks < k / 16; ++ks)
-        umma2(tmem, desc_kmajor(smem_u32(sa) + (ks / 4) * (128 * 128), ks % 4), desc_kmajor(smem_u32(sb) + (ks / 4) * (nh * 128), ks % 4),
-              idesc, ks != 0);
+      const uint32_t idesc = make_idesc(256, n, kF16, kF16, kMn ? 1 : 0, kMn ? 1 : 0);
+      for (int ks = 0; ks < k / 16; ++ks) {
+        if (kMn)
+          umma2(tmem, desc_mnmajor(smem_u32(sa), ks, k * 128), desc_mnmajor(smem_u32(sb), ks, k * 128), idesc, ks != 0);
+        else
+          umma2(tmem, desc_kmajor(smem_u32(sa) + (ks / 4) * (128 * 128), ks % 4), desc_kmajor(smem_u32(sb) + (ks / 4) * (nh * 128), ks % 4),
+                idesc, ks != 0);
+      }
       umma_commit2(smem_u32(&bar_done), 3);
     }
     __syncwarp();
@@ -223,16 +232,27 @@ __global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(unsigned long l
 
 }  // namespace nerf
 
-extern "C" int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream) {
+static int run_selftest2(float* d_out, const float* a, const float* b, int n, int k, bool mn, void* stream) {
   using namespace nerf;
-  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0, "selftest2: n must be a multiple of 64 in [64,256], got %d", n);
+  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % (mn ? 128 : 64) == 0, "selftest2: n must be a multiple of %d in [64,256], got %d", mn ? 128 : 64, n);
   NERF_CHECK_ARG(k >= 64 && k <= 256 && k % 64 == 0, "selftest2: k must be a multiple of 64 in [64,256], got %d", k);
   size_t smem = 1024 + size_t(128) * k * 2 + size_t(n / 2) * k * 2;
-  cudaError_t e = cudaFuncSetAttribute(selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = mn ? cudaFuncSetAttribute(selftest2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(selftest2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   NERF_CHECK_ARG(e == cudaSuccess, "selftest2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  selftest2_kernel<<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k);
+  if (mn)
+    selftest2_kernel<true><<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k);
+  else
+    selftest2_kernel<false><<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_out, a, b, n, k);
   NERF_CHECK_LAUNCH("selftest2_kernel");
   return 0;
+}
+
+extern "C" int nerf_selftest_umma2(float* d_out, const float* a, const float* b, int n, int k, void* stream) {
+  return run_selftest2(d_out, a, b, n, k, false, stream);
+}
+extern "C" int nerf_selftest_umma2_mn(float* d_out, const float* a, const float* b, int n, int k, void* stream) {
+  return run_selftest2(d_out, a, b, n, k, true, stream);
 }
 
 extern "C" int nerf_selftest_umma(float* d_out, const float* a, const float* b, int n, int k, int mode, void* stream) {

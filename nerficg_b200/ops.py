@@ -197,6 +197,16 @@ def mlp_backward(grads_flat: torch.Tensor, d_rgbsigma: torch.Tensor, rgbsigma: t
           'nerf_mlp_backward')
 
 
+def mlp_backward_legacy(grads_flat: torch.Tensor, d_rgbsigma: torch.Tensor, rgbsigma: torch.Tensor, stash: torch.Tensor,
+                        workspace: torch.Tensor, packed: torch.Tensor, params_flat: torch.Tensor, n_rays: int, n_samples: int,
+                        grad_scale: float = 1.0) -> None:
+    """K4, previous two-kernel path (tile-major dgrad chain + layer-major wgrad); kept for A/B timing and as a cross-check."""
+    require_device(grads_flat)
+    check(load().nerf_mlp_backward_legacy(ptr(grads_flat), ptr(d_rgbsigma), ptr(rgbsigma), ptr(stash), ptr(workspace), ptr(packed),
+                                          ptr(params_flat), n_rays, n_samples, float(grad_scale), stream_ptr()),
+          'nerf_mlp_backward_legacy')
+
+
 def mlp_backward_dgrad(d_rgbsigma, rgbsigma, stash, workspace, packed, params_flat, n_rays: int, n_samples: int) -> None:
     """K4a only: fills ``workspace`` with the per-layer output gradients."""
     require_device(d_rgbsigma)
@@ -222,11 +232,13 @@ def selftest_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
     return out
 
 
-def selftest_umma2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """D = A @ B^T on one 256-row tile through a cta_group::2 CTA pair (tests only)."""
+def selftest_umma2(a: torch.Tensor, b: torch.Tensor, mn_major: bool = False) -> torch.Tensor:
+    """D = A @ B^T on one 256-row tile through a cta_group::2 CTA pair (tests only); ``mn_major``: operands stored
+    reduction-major and read as MN-major (the weight-gradient flavour)."""
     a, b = _f32c(a), _f32c(b)
     require_device(a)
     assert a.shape[0] == 256 and a.shape[1] == b.shape[1]
     out = torch.empty((256, b.shape[0]), dtype=torch.float32, device=a.device)
-    check(load().nerf_selftest_umma2(ptr(out), ptr(a), ptr(b), b.shape[0], a.shape[1], stream_ptr()), 'nerf_selftest_umma2')
+    fn = load().nerf_selftest_umma2_mn if mn_major else load().nerf_selftest_umma2
+    check(fn(ptr(out), ptr(a), ptr(b), b.shape[0], a.shape[1], stream_ptr()), 'nerf_selftest_umma2')
     return out

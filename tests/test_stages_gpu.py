@@ -52,6 +52,18 @@ def _record_k2(name, frac, worst, numel):
         f.write(json.dumps({'test': 'K2_' + name, 'outlier_fraction_gt_2e-5': frac, 'max_abs': worst, 'samples': numel}) + '\n')
 
 
+@pytest.mark.parametrize('n,k', [(256, 128), (256, 64), (128, 128), (256, 256)])
+def test_umma_cta_pair_mn_major_selftest(ops, n, k):
+    """cta_group::2 MMAs with BOTH operands MN-major (stored reduction-major): the descriptor flavour of the fused
+    weight-gradient path (dW += dY^T X over the samples)."""
+    g = torch.Generator().manual_seed(3 * n + k)
+    a = torch.randn(256, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    ref = a.half().double() @ b.half().double().T
+    out = ops.selftest_umma2(a.to(DEV), b.to(DEV), mn_major=True).cpu()
+    assert torch.allclose(out.double(), ref, rtol=1e-4, atol=1e-3), (out.double() - ref).abs().max()
+
+
 def test_stratified_golden(ops, golden):
     g = golden('stratified')
     z = ops.sample_stratified(g['n'], g['nc'], g['near'], g['far'], g['u'].to(DEV), torch.device(DEV)).cpu()

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,power.limit,clocks.max.sm --format=csv > $OUT/gpu.tx
 for s in $STEPS; do
   case $s in
     tests)
-      timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_EXTRA:-} > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+      timeout 1500 python -m pytest tests -m gpu -q ${PYTEST_EXTRA:-} > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
       cp gpurun_out/parity_measured.jsonl $OUT/ 2>/dev/null; cp gpurun_out/grad_parity.jsonl $OUT/ 2>/dev/null;;
     variants)
       timeout 300 python tools/kernel_timing.py > $OUT/stall_base.txt 2>&1
@@ -21,6 +21,8 @@ for s in $STEPS; do
       timeout 600 python tools/stress_sweep.py > $OUT/stress.txt 2>&1;;
     bench)
       timeout 900 python bench.py ${BENCH_ARGS:-} > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err;;
+    pipecheck)
+      timeout 180 python tools/pipe_check.py > $OUT/pipe_check.txt 2>&1; echo "pipe_check rc=$?" >> $OUT/pipe_check.txt;;
     l2probe)
       timeout 300 python tools/l2_probe.py > $OUT/l2_probe.txt 2>&1;;
     ncuk2)
@@ -33,5 +35,6 @@ for s in $STEPS; do
 done
 tail -3 $OUT/pytest_gpu.log 2>/dev/null
 cat $OUT/l2_probe.txt 2>/dev/null
+cat $OUT/pipe_check.txt 2>/dev/null
 grep -h "^---" $OUT/stall_*.txt 2>/dev/null
 head -c 600 $OUT/bench.json 2>/dev/null
