@@ -252,8 +252,8 @@ def test_psnr_parity_trained_regime(fw):
     finally:
         Framework.config.TRAINING.NUM_ITERATIONS = 500000
     mean = sum(runs) / len(runs)
-    _record('psnr_parity_trained_regime', steps=steps, psnr_oracle_fp32=psnr_ref, psnr_oracle_fp32_init_perturbed_1e-6=psnr_ref_1e6,
-            psnr_oracle_fp32_init_perturbed_5e-4=psnr_ref_5e4, psnr_cuda_runs=runs, psnr_cuda_mean=mean,
+    _record('psnr_parity_trained_regime', steps=steps, psnr_oracle_fp32=psnr_ref, psnr_oracle_fp32_init_perturbed_1em6=psnr_ref_1e6,
+            psnr_oracle_fp32_init_perturbed_5em4=psnr_ref_5e4, psnr_cuda_runs=runs, psnr_cuda_mean=mean,
             teacher_forced_at_our_weights=sigma_probe)
     # teacher-forced bar (north star 1e-3 absolute): colour and depth meet it on every ray; alpha meets it at the 99.9th
     # percentile -- measured on B200 after 1500 steps (sigma_max 58): rgb max 7.9e-4, alpha max 1.4e-3 / p99.9 6.0e-4 /
