@@ -175,6 +175,10 @@ int nerf_selftest_umma2_mn(float* d_out, const float* a, const float* b, int n, 
  * (mode 0: 32x32b.x32, 1: two x32 in flight, 2: x16); out[0] = cycles, out[1] = bytes read from TMEM. */
 int nerf_selftest_tmem_read(unsigned long long* out, int n_warps, int mode, int iters, void* stream);
 
+/* Tensor-pipe rate probe (development aid): `iters` back-to-back cta_group::2 M256 N256 K16 MMAs, K-major or MN-major operands;
+ * out[0] = cycles. */
+int nerf_selftest_umma2_rate(unsigned long long* out, int mn_major, int iters, void* stream);
+
 /* L2 -> SM streaming probe (development aid): n_ctas CTAs each move `iters` 16 KB chunks between an L2-resident window and
  * shared memory with 1-D bulk copies (mode bit 0: loads, bit 1: stores); out[0] = cycles of the slowest CTA, out[1] = bytes per CTA. */
 int nerf_selftest_l2_stream(unsigned long long* out, void* window, uint32_t window_bytes, int mode, int iters, int n_ctas, void* stream);

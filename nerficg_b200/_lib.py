@@ -46,6 +46,7 @@ _PROTOTYPES = {
     'nerf_selftest_umma2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nerf_selftest_umma2_mn': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nerf_selftest_tmem_read': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    'nerf_selftest_umma2_rate': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'nerf_selftest_l2_stream': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_void_p]),
     'nerf_selftest_l2_stream_lsu': (c_int, [c_void_p, c_void_p, ctypes.c_uint32, c_int, c_int, c_int, c_int, c_void_p]),
 }

@@ -505,15 +505,16 @@ static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbs
 extern "C" int nerf_mlp_backward_pipe(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
                                       const void* packed, const float* params, int n_rays, int n_samples, float grad_scale, void* stream);
 
-// The production backward is the layer-stationary pipeline (mlp_bwd_pipe.cu).  The two-kernel path (tile-major dgrad chain +
-// layer-major wgrad) stays available: as the *_dgrad / *_wgrad phases below and, fused, as nerf_mlp_backward_legacy.
+// The production backward is the two-kernel path (tile-major dgrad chain + layer-major wgrad).  The layer-stationary fused pipeline
+// (mlp_bwd_pipe.cu) computes the same gradients with half the HBM traffic but is, as measured in round 2, ring-depth-bound and
+// slower; it stays exported as nerf_mlp_backward_pipe and can be made the default with -DNERF_BWD_PIPE.
 extern "C" int nerf_mlp_backward(float* grads, const float* d_rgbsigma, const float* rgbsigma, const void* stash, void* workspace,
                                  const void* packed, const float* params, int n_rays, int n_samples, float grad_scale,
                                  void* stream) {
-#ifdef NERF_BWD_LEGACY
-  return run_backward(grads, d_rgbsigma, rgbsigma, stash, workspace, packed, params, n_rays, n_samples, grad_scale, stream, 3);
-#else
+#ifdef NERF_BWD_PIPE
   return nerf_mlp_backward_pipe(grads, d_rgbsigma, rgbsigma, stash, workspace, packed, params, n_rays, n_samples, grad_scale, stream);
+#else
+  return run_backward(grads, d_rgbsigma, rgbsigma, stash, workspace, packed, params, n_rays, n_samples, grad_scale, stream, 3);
 #endif
 }
 

@@ -41,14 +41,14 @@ constexpr int kLinks = 8;                     // link k feeds stage k + 1
 constexpr int kLinkSlots = 4;
 constexpr uint32_t kStageBytes = kPanelBytes128;   // 16 KB ring stage
 constexpr uint32_t kHalfPanel = 8192;
-constexpr int kRing = 6;
+constexpr int kRing = 8;
 constexpr uint32_t kGroupBytes = 2 * kActBytes;    // one link slot: two tile images
 // shared memory map of a stage CTA
 constexpr uint32_t kOffW = 0;                                   // 4 x 16 KB: this CTA's half of the layer's W^T panels
-constexpr uint32_t kOffRing = kOffW + kActBytes;                // 6 x 16 KB
-constexpr uint32_t kOffOut = kOffRing + kRing * kStageBytes;    // 64 KB: dY_out image (4 panels)
-constexpr uint32_t kOffBars = kOffOut + kActBytes;
-constexpr uint32_t kOffDsig = kOffBars + 512;                   // 64 floats: dsigma_raw of the half tile in flight (stage F)
+constexpr uint32_t kOffRing = kOffW + kActBytes;                // 8 x 16 KB
+constexpr uint32_t kOffOut = kOffRing + kRing * kStageBytes;    // 32 KB: two panels of the dY_out image (one 128-column phase)
+constexpr uint32_t kOffBars = kOffOut + 2 * kPanelBytes128;
+constexpr uint32_t kOffDsig = kOffBars + 512;                   // 128 floats: dsigma_raw of the tile in flight (stage F)
 constexpr uint32_t kSmemBytes = kOffDsig + 512;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 // shared memory map of a head CTA: W (2 x 16 KB) | dG operand of slot 0, 1 (2 x 32 KB) | dF image of slot 0, 1 (2 x 64 KB)
@@ -74,6 +74,7 @@ struct PipeParams {
   int64_t n_evals;
   int n_tiles;
   float inv_scale;
+  unsigned long long* prof;   // optional stall counters (tools/pipe_timing.py), see the slot list at the end of the kernel
 };
 
 // ---- flags (gpu scope) ------------------------------------------------------------------------------------------------
@@ -85,10 +86,15 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t target) {
-  while (ld_acquire_gpu(p) < target) __nanosleep(64);
+// plain (relaxed) add: used to hand a link slot BACK -- the reads it covers have completed (their mbarrier flipped), nothing is published
+__device__ __forceinline__ void red_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t target) {
+  while (ld_acquire_gpu(p) < target) __nanosleep(32);
+}
+#define PIPE_TIMED(acc, stmt) NERF_TIMED(prof_on, acc, stmt)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // 16 columns of a dgrad epilogue (as in mlp_bwd.cu): t = acc (+ dsigma_raw * w_sigma), masked by the forward's ReLU bits
 template <bool kSig>
@@ -160,7 +166,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
   const uint32_t bar_acc_free = bar_acc_ready + 16;        // leader only, count 16: accumulator drained by both CTAs
   const uint32_t bar_a_ready = bar_acc_free + 8;           // [2] head, leader only, count 16: dG operands written
   const uint32_t bar_img_full = bar_a_ready + 16;          // count 8: dY_out image complete in shared memory
-  const uint32_t bar_img_empty = bar_img_full + 8;         // count 2: copied out by the two store warps
+  const uint32_t bar_img_empty = bar_img_full + 8;         // count 4: read out of shared memory by the four store warps
   const uint32_t bar_done = bar_img_empty + 8;             // every MMA of this pair has completed (multicast commit)
   const uint32_t tmem_slot = bar_done + 8;
 
@@ -179,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
     mbar_init(bar_a_ready, 16);
     mbar_init(bar_a_ready + 8, 16);
     mbar_init(bar_img_full, 8);
-    mbar_init(bar_img_empty, 2);
+    mbar_init(bar_img_empty, 4);
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
@@ -194,6 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
+  const bool prof_on = p.prof != nullptr;
   const uint8_t* wimg = p.packed + kBwdImageOffset;
   auto link_base = [&](int k, int slot) -> uint8_t* { return p.links + ((size_t)(pl * kLinks + k) * kLinkSlots + slot) * kGroupBytes; };
   auto flag_ready = [&](int k, int slot) -> uint32_t* { return p.flags + ((size_t)(pl * kLinks + k) * kLinkSlots + slot) * kFlagStride; };
@@ -262,6 +269,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
       const uint32_t out_h = out_smem + 2 * half * kPanelBytes128 + row_off;
       const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
       uint32_t acc_phase = 0;
+      long long h_acc = 0, h_freed = 0, h_store = 0;
+      const long long h_begin = prof_on ? clock64() : 0;
       for (int t = slot; t < n_mine; t += 2) {
         const int group = pl + kPipelines * t;
         const int tile = group * 2 + (int)rank;
@@ -337,7 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
           }
         }
         // ---- dF = dG W_c0[:, :256] (no mask: f is linear) -> fp16 image -> link 0 ----
-        mbar_wait(bar_acc_ready + 8 * slot, acc_phase);
+        PIPE_TIMED(h_acc, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
         {
@@ -349,16 +358,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
         named_bar_sync(bar_id, 256);
         if (tg == 0) {
           const int ls = t % kLinkSlots, use = t / kLinkSlots;
-          spin_until(flag_freed(0, ls), 2u * (uint32_t)use);          // both consumer CTAs have released the slot's previous group
+          PIPE_TIMED(h_freed, spin_until(flag_freed(0, ls), 2u * (uint32_t)use));   // both consumer CTAs have released the slot's previous group
           bulk_s2g(link_base(0, ls) + rank * kActBytes, out_smem, kActBytes);
           bulk_commit();
-          bulk_wait_all<0>();                                           // writes complete (not only read) before the flag
+          PIPE_TIMED(h_store, bulk_wait_all<0>());                      // writes complete (not only read) before the flag
           fence_proxy_async_all();
           __threadfence();
-          red_release_gpu(flag_ready(0, ls), 2u);                       // (stage producers add 1 per store warp: 4 per group either way)
+          red_release_gpu(flag_ready(0, ls), 1u);                       // one per CTA: consumers wait for 2 per group
         }
       }
       if (tg == 0) bulk_wait_all<0>();
+      if (prof_on && tg == 0) {
+        atomicAdd(p.prof + 13, (unsigned long long)(clock64() - h_begin));
+        atomicAdd(p.prof + 14, (unsigned long long)h_freed);
+        atomicAdd(p.prof + 15, (unsigned long long)h_store);
+        atomicAdd(p.prof + 16, (unsigned long long)h_acc);
+        atomicAdd(p.prof + 20, 1ull);
+        atomicAdd(p.prof + 32 + 0, (unsigned long long)h_freed);
+      }
     }
   } else {
     // ==================================================================================================================
@@ -367,68 +384,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
     const int st = role;                         // 1 = F, 2..8 = hidden layers 7..1 (chain stage numbering of mlp_bwd.cu)
     const int k_in = st - 1;                     // input link
     const int h_region = kStashH0 + (8 - st);    // activations that fed this layer: h7, h6, ..., h0
+    // Ring positions of one group (all 16 KB = one whole 128-row panel, ONE bulk copy each: the TMA unit of an SM retires one
+    // 1-D bulk copy per ~259 cycles whatever its size up to 16 KB, measured with tools/l2_probe.py):
+    //   0..3   A0..A3    this CTA's tile of dY_in, K panels 0..3                                   (dgrad operand, K-major)
+    //   4, 5   Xa, Xb    tile 0 of the pair: dY_in panels 2 rank, 2 rank + 1  \  wgrad operands, MN-major, K = the 128 samples
+    //   6, 7   Ya, Yb    tile 0: activation panels 2 rank, 2 rank + 1         /  of the tile; (Xa, Xb) and (Ya, Yb) are adjacent
+    //   8..11            the same for tile 1                                       ring stages = one 128-column operand each
     if (warp < 4) {
       setmaxnreg_dec<kRegsOther>();
-      if (warp == 0) {
-        // ------------------------------------------------ loader ------------------------------------------------
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bar_w_full, 4 * kStageBytes);
-          for (int pp = 0; pp < 4; ++pp)
-            bulk_g2s_hint(smem_base + kOffW + pp * kStageBytes, wimg + (uint32_t)(bwd_first_panel(st) + pp) * kPanelBytes256 + rank * kStageBytes,
-                          kStageBytes, bar_w_full, l2_evict_last());
-        }
-        __syncwarp();
-        const uint64_t pol_stream = l2_evict_first();
-        uint32_t stage = 0, phase = 0;
-        auto next_stage = [&]() {
-          if (++stage == (uint32_t)kRing) {
-            stage = 0;
-            phase ^= 1;
+      if (warp != 1) {
+        // ------------------------------------------------ loaders (warps 0, 2, 3) ------------------------------------------------
+        const int wl = warp == 0 ? 0 : warp - 1;   // 0, 1, 2: in-group positions wl, wl + 3, wl + 6, wl + 9
+        if (wl == 0) {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_w_full, 4 * kStageBytes);
+            for (int pp = 0; pp < 4; ++pp)
+              bulk_g2s_hint(smem_base + kOffW + pp * kStageBytes, wimg + (uint32_t)(bwd_first_panel(st) + pp) * kPanelBytes256 + rank * kStageBytes,
+                            kStageBytes, bar_w_full, l2_evict_last());
           }
-        };
+          __syncwarp();
+        }
+        const uint64_t pol_stream = l2_evict_first();
+        const long long l_begin = prof_on ? clock64() : 0;
+        long long l_flag = 0, l_empty = 0, l_fence = 0, l_issue = 0;
         for (int t = 0; t < n_mine; ++t) {
           const int group = pl + kPipelines * t;
           const int ls = t % kLinkSlots, use = t / kLinkSlots;
           if (elect_one()) {
-            spin_until(flag_ready(k_in, ls), 4u * (uint32_t)(use + 1));
-            fence_proxy_async_all();                 // the bulk loads below (async proxy) must observe the producer's data
+            PIPE_TIMED(l_flag, spin_until(flag_ready(k_in, ls), 2u * (uint32_t)(use + 1)));
+            PIPE_TIMED(l_fence, fence_proxy_async_all());   // the bulk loads below (async proxy) must observe the producer's data
           }
           __syncwarp();
           const uint8_t* lbase = link_base(k_in, ls);
-          // dgrad operand: this CTA's tile, K panels 0..3
-          for (int pp = 0; pp < 4; ++pp) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          for (int i = wl; i < 12; i += 3) {
+            const uint32_t pos = 12u * (uint32_t)t + (uint32_t)i;
+            const uint32_t stage = pos % (uint32_t)kRing, phase = (pos / (uint32_t)kRing) & 1u;
+            PIPE_TIMED(l_empty, mbar_wait(bar_empty + 8 * stage, phase ^ 1));
+            const long long i0 = prof_on ? clock64() : 0;
             if (elect_one()) {
               mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-              bulk_g2s(smem_base + kOffRing + stage * kStageBytes, lbase + rank * kActBytes + pp * kPanelBytes128, kStageBytes, bar_full + 8 * stage);
-            }
-            __syncwarp();
-            next_stage();
-          }
-          // wgrad operands: K = the 64-sample halves of tile q; this CTA's 128 feature columns = panels 2 rank, 2 rank + 1
-          for (int q = 0; q < 2; ++q) {
-            int tile_q = group * 2 + q;
-            if (tile_q >= p.n_tiles) tile_q = p.n_tiles - 1;   // (its dY is all zero: any finite activations will do)
-            const uint8_t* hbase = p.stash + stash_region_offset(h_region, n_tiles64) + (uint64_t)tile_q * kActBytes;
-            for (int h = 0; h < 2; ++h) {
-              for (int xy = 0; xy < 2; ++xy) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                if (elect_one()) {
-                  mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-                  const uint32_t dst = smem_base + kOffRing + stage * kStageBytes;
-                  for (int i = 0; i < 2; ++i) {
-                    const uint32_t off = (uint32_t)(2 * rank + i) * kPanelBytes128 + (uint32_t)h * kHalfPanel;
-                    if (xy == 0) bulk_g2s(dst + i * kHalfPanel, lbase + q * kActBytes + off, kHalfPanel, bar_full + 8 * stage);
-                    else bulk_g2s_hint(dst + i * kHalfPanel, hbase + off, kHalfPanel, bar_full + 8 * stage, pol_stream);
-                  }
+              const uint32_t dst = smem_base + kOffRing + stage * kStageBytes;
+              if (i < 4) {
+                bulk_g2s(dst, lbase + rank * kActBytes + i * kPanelBytes128, kStageBytes, bar_full + 8 * stage);
+              } else {
+                const int q = (i - 4) >> 2, xy = ((i - 4) >> 1) & 1, j = i & 1;
+                const uint32_t off = (uint32_t)(2 * rank + j) * kPanelBytes128;
+                if (xy == 0) {
+                  bulk_g2s(dst, lbase + q * kActBytes + off, kStageBytes, bar_full + 8 * stage);
+                } else {
+                  int tile_q = group * 2 + q;
+                  if (tile_q >= p.n_tiles) tile_q = p.n_tiles - 1;   // (its dY is all zero: any finite activations will do)
+                  bulk_g2s_hint(dst, p.stash + stash_region_offset(h_region, n_tiles64) + (uint64_t)tile_q * kActBytes + off, kStageBytes,
+                                bar_full + 8 * stage, pol_stream);
                 }
-                __syncwarp();
-                next_stage();
               }
             }
+            __syncwarp();
+            if (prof_on) l_issue += clock64() - i0;
           }
         }
-      } else if (warp == 1) {
+        if (prof_on && lane == 0 && rank == 0 && wl == 0) {
+          atomicAdd(p.prof + 0, (unsigned long long)l_flag);
+          atomicAdd(p.prof + 1, (unsigned long long)l_empty);
+          atomicAdd(p.prof + 21, (unsigned long long)l_fence);
+          atomicAdd(p.prof + 22, (unsigned long long)(clock64() - l_begin));
+          atomicAdd(p.prof + 23, (unsigned long long)l_issue);
+          atomicAdd(p.prof + 32 + 3 * role + 0, (unsigned long long)l_flag);
+        }
+      } else {
         // ------------------------------------------------ MMA issuer (leader) / relay (peer) ------------------------------------------------
         const bool leader = rank == 0;
         constexpr uint32_t idesc_d = make_idesc(256, 256, kF16, kF16, 0, 0);
@@ -441,6 +464,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
           __syncwarp();
         }
         uint32_t stage = 0, phase = 0, free_phase = 0;
+        long long m_free = 0, m_full = 0, m_full_w = 0;
+        bool in_wgrad = false;
+        const long long m_begin = prof_on ? clock64() : 0;
         auto next_stage = [&]() {
           if (++stage == (uint32_t)kRing) {
             stage = 0;
@@ -449,19 +475,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
         };
         // the stage's operands have landed in BOTH CTAs (leader) / in this CTA, announced to the leader (peer)
         auto stage_ready = [&]() {
+          const long long w0 = prof_on ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
-          if (leader) mbar_wait_cluster(bar_peer + 8 * stage, phase);
-          else {
+          if (leader) {
+            mbar_wait_cluster(bar_peer + 8 * stage, phase);
+          } else {
             if (elect_one()) mbar_arrive_cluster(mapa(bar_peer + 8 * stage, 0));
             __syncwarp();
           }
+          if (prof_on) (in_wgrad ? m_full_w : m_full) += clock64() - w0;
         };
         for (int t = 0; t < n_mine; ++t) {
           const int ls = t % kLinkSlots;
           if (leader && t > 0) {   // the accumulator of the previous group has been drained by both CTAs
-            mbar_wait_cluster(bar_acc_free, free_phase);
+            PIPE_TIMED(m_free, mbar_wait_cluster(bar_acc_free, free_phase));
             free_phase ^= 1;
           }
+          in_wgrad = false;
           for (int pp = 0; pp < 4; ++pp) {
             stage_ready();
             if (leader) {
@@ -478,27 +508,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
             }
             next_stage();
           }
-          for (int c = 0; c < 4; ++c) {
-            stage_ready();
-            const uint32_t sx = stage;
-            next_stage();
-            stage_ready();
-            const uint32_t sy = stage;
-            next_stage();
-            if (c == 3) {   // every load from the input link slot has landed in this CTA: give the slot back to the producer
-              if (elect_one()) red_release_gpu(flag_freed(k_in, ls), 1u);
-              __syncwarp();
+          in_wgrad = true;
+          for (int q = 0; q < 2; ++q) {
+            uint32_t sidx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // Xa, Xb, Ya, Yb
+              stage_ready();
+              sidx[i] = stage;
+              next_stage();
             }
             if (leader) {
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t ax = smem_base + kOffRing + sx * kStageBytes, by = smem_base + kOffRing + sy * kStageBytes;
+                const uint32_t ax = smem_base + kOffRing + sidx[0] * kStageBytes, by = smem_base + kOffRing + sidx[2] * kStageBytes;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma2(dw, desc_mnmajor(ax, ks, kHalfPanel), desc_mnmajor(by, ks, kHalfPanel), idesc_w, (t | c | ks) != 0);
-                umma_commit2(bar_empty + 8 * sx, 3);
-                umma_commit2(bar_empty + 8 * sy, 3);
+                for (int ks = 0; ks < 8; ++ks)   // 8 x 16 samples; the two 64-column groups of an operand are one ring stage apart
+                  umma2(dw, desc_mnmajor(ax, ks, kStageBytes), desc_mnmajor(by, ks, kStageBytes), idesc_w, (t | q | ks) != 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) umma_commit2(bar_empty + 8 * sidx[i], 3);
               }
+              __syncwarp();
+            }
+            if (q == 1) {   // every load from the input link slot has landed in this CTA: give the slot back to the producer
+              if (elect_one()) red_relaxed_gpu(flag_freed(k_in, ls), 1u);
               __syncwarp();
             }
           }
@@ -506,47 +538,105 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
         if (leader) {
           if (elect_one()) umma_commit2(bar_done, 3);
           __syncwarp();
+          if (prof_on && lane == 0) {
+            atomicAdd(p.prof + 2, (unsigned long long)m_free);
+            atomicAdd(p.prof + 3, (unsigned long long)m_full);
+            atomicAdd(p.prof + 4, (unsigned long long)m_full_w);
+            atomicAdd(p.prof + 5, (unsigned long long)(clock64() - m_begin));
+            atomicAdd(p.prof + 19, 1ull);
+            atomicAdd(p.prof + 32 + 3 * role + 1, (unsigned long long)(m_full + m_full_w));
+          }
         }
       }
     } else if (warp < 12) {
-      // ------------------------------------------------ epilogue: acc -> mask -> fp16 image ------------------------------------------------
+      // ------------------------------------------------ epilogue: acc -> mask -> fp16 image, two 128-column phases ------------------------
+      // The image buffer holds two panels (32 KB): phase ph converts accumulator columns [128 ph, +128) -- warp (quarter, hh) takes the
+      // 64 columns of panel hh -- and hands them to the store warps, so a group is two image events.
       setmaxnreg_inc<kRegsEpilogue>();
       const int ew = warp - 4;
-      const int half = (ew >> 2) & 1;
+      const int hh = (ew >> 2) & 1;
       const int wq = warp & 3;
       const int row = wq * 32 + lane;
-      const uint32_t t_acc = tmem_base + half * 128 + (static_cast<uint32_t>(wq * 32) << 16);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
       const uint32_t row_off = (uint32_t)(row >> 3) * kAtomBytes + (uint32_t)(row & 7) * kPanelRowBytes;
       const uint32_t xr = (uint32_t)(row & 7) << 4;
-      const uint32_t out_h = smem_base + kOffOut + 2 * half * kPanelBytes128 + row_off;
+      const uint32_t out_p = smem_base + kOffOut + hh * kPanelBytes128 + row_off;
       const uint32_t acc_free_leader = mapa(bar_acc_free, 0);
       const int mask_layer = 8 - st;
-      const float* wsp = p.params + L::kWS + 128 * half;
-      uint32_t acc_phase = 0;
+      uint32_t acc_phase = 0, ev = 0;   // ev = image events handed over so far
+      long long e_acc = 0, e_img = 0;
+      const long long e_begin = prof_on ? clock64() : 0;
+      const bool e_prof = prof_on && rank == 0 && warp == 4 && lane == 0;
       for (int t = 0; t < n_mine; ++t) {
         const int group = pl + kPipelines * t;
         const int tile = group * 2 + (int)rank;
         const bool tile_ok = tile < p.n_tiles;
         const int64_t e = (int64_t)tile * kTile + row;
-        uint4 mk4 = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (tile_ok)
-          mk4 = __ldg(reinterpret_cast<const uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
-                                                     (uint64_t)tile * stash_region_tile_bytes(kStashMask) + mask_layer * (128 * 32) + row * 32 + half * 16));
+        // ReLU bits of the row's 256 columns: word w = columns [32 w, 32 w + 32) (tc.cuh relu_mask_bit order); this warp needs words
+        // 4 ph + 2 hh, + 1 in phase ph
+        uint2 mph[2] = {make_uint2(~0u, ~0u), make_uint2(~0u, ~0u)};
+        if (tile_ok) {
+          const uint8_t* mp = p.stash + stash_region_offset(kStashMask, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(kStashMask) +
+                              mask_layer * (128 * 32) + row * 32 + 8 * hh;
+          mph[0] = __ldg(reinterpret_cast<const uint2*>(mp));
+          mph[1] = __ldg(reinterpret_cast<const uint2*>(mp + 16));
+        }
         float dsr = 0.f;
         if (st == 1 && tile_ok && e < p.n_evals) dsr = __ldg(p.d_rgbsigma + e).w;
-        mbar_wait(bar_acc_ready, acc_phase);
+        PIPE_TIMED(e_acc, mbar_wait(bar_acc_ready, acc_phase));
         acc_phase ^= 1;
         tc_fence_after();
-        if (t > 0) mbar_wait(bar_img_empty, (uint32_t)(t - 1) & 1u);   // the previous image has been copied out of kOffOut
-        const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-        if (st == 1) pipe_drain_acc<true>(t_acc, mk, wsp, dsr, out_h, xr);
-        else pipe_drain_acc<false>(t_acc, mk, wsp, dsr, out_h, xr);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(acc_free_leader);   // accumulator drained (tcgen05.wait::ld of every chunk has retired)
-          mbar_arrive(bar_img_full);
+#ifdef NERF_PIPE_EXP_NOEPI
+        for (int ph = 0; ph < 2; ++ph) {
+          if (ev > 0) mbar_wait(bar_img_empty, (ev - 1) & 1u);
+          if (ph == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_free_leader);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_img_full);
+          ++ev;
         }
+        continue;
+#endif
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          const int col0 = 128 * ph + 64 * hh;                       // first accumulator column of this warp in this phase
+          const float* wsp = p.params + L::kWS + col0;
+          const uint32_t w0m = ph == 0 ? mph[0].x : mph[1].x, w1m = ph == 0 ? mph[0].y : mph[1].y;
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_row + col0, va);
+          if (ev > 0) PIPE_TIMED(e_img, mbar_wait(bar_img_empty, (ev - 1) & 1u));   // the previous image has left the buffer
+          tmem_ld_wait16(va);
+          tmem_ld16(t_row + col0 + 16, vb);
+          if (st == 1) pipe_dgrad16<true>(va, w0m, 0, wsp, dsr, out_p + (0u ^ xr), out_p + (16u ^ xr));
+          else pipe_dgrad16<false>(va, w0m, 0, wsp, dsr, out_p + (0u ^ xr), out_p + (16u ^ xr));
+          tmem_ld_wait16(vb);
+          tmem_ld16(t_row + col0 + 32, va);
+          if (st == 1) pipe_dgrad16<true>(vb, w0m, 8, wsp + 16, dsr, out_p + (32u ^ xr), out_p + (48u ^ xr));
+          else pipe_dgrad16<false>(vb, w0m, 8, wsp + 16, dsr, out_p + (32u ^ xr), out_p + (48u ^ xr));
+          tmem_ld_wait16(va);
+          tmem_ld16(t_row + col0 + 48, vb);
+          if (st == 1) pipe_dgrad16<true>(va, w1m, 0, wsp + 32, dsr, out_p + (64u ^ xr), out_p + (80u ^ xr));
+          else pipe_dgrad16<false>(va, w1m, 0, wsp + 32, dsr, out_p + (64u ^ xr), out_p + (80u ^ xr));
+          tmem_ld_wait16(vb);
+          if (ph == 1) {   // the accumulator has been read completely: the next group's dgrad MMAs may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_free_leader);
+          }
+          if (st == 1) pipe_dgrad16<true>(vb, w1m, 8, wsp + 48, dsr, out_p + (96u ^ xr), out_p + (112u ^ xr));
+          else pipe_dgrad16<false>(vb, w1m, 8, wsp + 48, dsr, out_p + (96u ^ xr), out_p + (112u ^ xr));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_img_full);
+          ++ev;
+        }
+      }
+      if (e_prof) {
+        atomicAdd(p.prof + 6, (unsigned long long)e_acc);
+        atomicAdd(p.prof + 7, (unsigned long long)e_img);
+        atomicAdd(p.prof + 8, (unsigned long long)(clock64() - e_begin));
       }
       // ---- flush this CTA's half of dW (rows 128 rank .. +128 = output neurons, 256 columns = input features) ----
       mbar_wait(bar_done, 0);
@@ -555,8 +645,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
         const int layer = 8 - st + 1;   // st = 1 -> feature layer, st = 2..8 -> hidden layers 7..1
         const int64_t w_off = st == 1 ? L::kWF : L::hidden_w(layer);
         const int ld = st == 1 ? 256 : L::hidden_in(layer);
-        float* wrow = p.grads + w_off + (int64_t)(128 * rank + row) * ld + 128 * half;
-        const uint32_t t_dw = tmem_base + 256 + half * 128 + (static_cast<uint32_t>(wq * 32) << 16);
+        float* wrow = p.grads + w_off + (int64_t)(128 * rank + row) * ld + 128 * hh;
+        const uint32_t t_dw = t_row + 256 + hh * 128;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t v[32];
@@ -569,13 +659,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
       tc_fence_before();
     } else if (warp < 16) {
       // ------------------------------------------------ reducers: bias (and density-head) gradients ------------------------------------------------
-      // Every ring stage is visited in the loader's order; the X stages (dY_in: 64 samples x this CTA's 128 columns) feed the
-      // column sums, and in stage F the Y stages (h7) feed dL/dw_sigma.  A consumer arrives on `empty` only after the stage's
+      // Every ring position is visited in the loaders' order; the X stages (dY_in: 128 samples x 64 of this CTA's columns) feed
+      // the column sums, and in stage F the Y stages (h7) feed dL/dw_sigma.  A consumer arrives on `empty` only after the stage's
       // `full` phase: the barrier counts two arrivals per use (MMA commit + this group) and must never see two of one kind.
       const int tr = threadIdx.x - 12 * 32;      // 0..127
-      const int cp = tr & 63;                    // column pair 2 cp, 2 cp + 1 of the 128
-      const int rh = tr >> 6;                    // rows [32 rh, 32 rh + 32) of the 64
-      float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f, dsum = 0.f;
+      const int cg = tr & 7;                     // 16-byte chunk = columns [8 cg, 8 cg + 8) of the panel's 64
+      const int rg = tr >> 3;                    // rows [8 rg, 8 rg + 8) of the 128
+      // (one LDS.128 per row: a first version with 4-byte loads took ~700 cycles per stage -- ~1,000 with the density head -- and,
+      //  because `empty` needs this group's arrival, throttled the whole pipeline to stage F's reducers)
+      float sb[2][8], sd[2][8], dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sb[j][e] = sd[j][e] = 0.f;
       float* dsig = reinterpret_cast<float*>(smem_raw + kOffDsig);
       uint32_t stage = 0, phase = 0;
       auto next_stage = [&]() {
@@ -584,51 +680,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
           phase ^= 1;
         }
       };
-      auto col_base = [&](uint32_t s) { return smem_base + kOffRing + s * kStageBytes + (uint32_t)(cp >> 5) * kHalfPanel; };
+      auto load8 = [&](uint32_t addr, float (&f)[8]) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+        const float2 a0 = __half22float2(*reinterpret_cast<__half2*>(&w0)), a1 = __half22float2(*reinterpret_cast<__half2*>(&w1));
+        const float2 a2 = __half22float2(*reinterpret_cast<__half2*>(&w2)), a3 = __half22float2(*reinterpret_cast<__half2*>(&w3));
+        f[0] = a0.x; f[1] = a0.y; f[2] = a1.x; f[3] = a1.y; f[4] = a2.x; f[5] = a2.y; f[6] = a3.x; f[7] = a3.y;
+      };
+      // The ring (128 KB) cannot cover HBM latency at this operand rate (192 KB per group): measured, every group paid two HBM
+      // round trips in series.  The activation panels of the groups ahead are therefore pulled into L2 here (64 KB per group and
+      // CTA, one 128-byte line per prefetch), so that every ring load is an L2 hit.
+      constexpr int kPrefetchAhead = 3;
+      auto prefetch_group = [&](int tt) {
+        if (tt >= n_mine) return;
+        const int g2 = pl + kPipelines * tt;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          int tile_q = g2 * 2 + q;
+          if (tile_q >= p.n_tiles) tile_q = p.n_tiles - 1;
+          const uint8_t* hb = p.stash + stash_region_offset(h_region, n_tiles64) + (uint64_t)tile_q * kActBytes + (uint32_t)(2 * rank) * kPanelBytes128;
+#pragma unroll
+          for (int l = 0; l < 2; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(hb + (size_t)(tr + 128 * l) * 128));   // 2 panels = 256 lines
+        }
+      };
+      for (int tt = 0; tt < kPrefetchAhead; ++tt) prefetch_group(tt);
       for (int t = 0; t < n_mine; ++t) {
         const int group = pl + kPipelines * t;
-        for (int pp = 0; pp < 4; ++pp) {
+        prefetch_group(t + kPrefetchAhead);
+        for (int i = 0; i < 12; ++i) {
           mbar_wait(bar_full + 8 * stage, phase);
-          named_bar_sync(3, 128);
-          if (tr == 0) mbar_arrive(bar_empty + 8 * stage);
-          next_stage();
-        }
-        for (int c = 0; c < 4; ++c) {
-          // X: dY_in
-          mbar_wait(bar_full + 8 * stage, phase);
-          {
-            const uint32_t base = col_base(stage);
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + panel_offset(32 * rh + r, (2 * cp) & 63)));
-              const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-              s0 += f.x;
-              s1 += f.y;
-            }
-          }
-          if (st == 1) {   // dsigma_raw of the 64 samples of this half tile (zero beyond the batch)
-            if (tr < 64) {
-              const int64_t em = (int64_t)(group * 2 + (c >> 1)) * kTile + 64 * (c & 1) + tr;
-              dsig[tr] = em < p.n_evals ? __ldg(p.d_rgbsigma + em).w : 0.f;
-            }
-          }
-          named_bar_sync(3, 128);
-          if (tr == 0) mbar_arrive(bar_empty + 8 * stage);
-          next_stage();
-          // Y: activations
-          mbar_wait(bar_full + 8 * stage, phase);
-          if (st == 1) {
-            const uint32_t base = col_base(stage);
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + panel_offset(32 * rh + r, (2 * cp) & 63)));
-              const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-              const float ds = dsig[32 * rh + r];
-              d0 = fmaf(ds, f.x, d0);
-              d1 = fmaf(ds, f.y, d1);
-              if (cp == 0) dsum += ds;
+#ifdef NERF_PIPE_EXP_NORED
+          if (false) {
+#else
+          if (i >= 4) {
+#endif
+            const int q = (i - 4) >> 2, xy = ((i - 4) >> 1) & 1, j = i & 1;
+            const uint32_t base = smem_base + kOffRing + stage * kStageBytes;
+            if (xy == 0) {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                float f[8];
+                load8(base + panel_chunk_offset(8 * rg + r, cg), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  if (j == 0) sb[0][e] += f[e]; else sb[1][e] += f[e];
+                }
+              }
+              if (st == 1 && j == 0) {   // dsigma_raw of the tile's 128 samples (zero beyond the batch), used by the Y stages below
+                const int64_t em = (int64_t)(group * 2 + q) * kTile + tr;
+                dsig[tr] = em < p.n_evals ? __ldg(p.d_rgbsigma + em).w : 0.f;
+              }
+            } else if (st == 1) {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                float f[8];
+                load8(base + panel_chunk_offset(8 * rg + r, cg), f);
+                const float ds = dsig[8 * rg + r];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  if (j == 0) sd[0][e] = fmaf(ds, f[e], sd[0][e]); else sd[1][e] = fmaf(ds, f[e], sd[1][e]);
+                }
+                if (cg == 0 && j == 0) dsum += ds;
+              }
             }
           }
           named_bar_sync(3, 128);
@@ -639,44 +752,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pipe::kThreads, 1) m
       {
         const int layer = 8 - st + 1;
         const int64_t b_off = st == 1 ? L::kBF : L::hidden_b(layer);
-        atomicAdd(p.grads + b_off + 128 * rank + 2 * cp, s0 * p.inv_scale);
-        atomicAdd(p.grads + b_off + 128 * rank + 2 * cp + 1, s1 * p.inv_scale);
-        if (st == 1) {
-          atomicAdd(p.grads + L::kWS + 128 * rank + 2 * cp, d0 * p.inv_scale);
-          atomicAdd(p.grads + L::kWS + 128 * rank + 2 * cp + 1, d1 * p.inv_scale);
-          if (cp == 0 && rank == 0) atomicAdd(p.grads + L::kBS, dsum * p.inv_scale);   // (both CTAs see all 256 samples)
-        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            atomicAdd(p.grads + b_off + 128 * rank + 64 * j + 8 * cg + e, sb[j][e] * p.inv_scale);
+            if (st == 1) atomicAdd(p.grads + L::kWS + 128 * rank + 64 * j + 8 * cg + e, sd[j][e] * p.inv_scale);
+          }
+        if (st == 1 && cg == 0 && rank == 0) atomicAdd(p.grads + L::kBS, dsum * p.inv_scale);   // (both CTAs see all 256 samples)
       }
-    } else if (warp < 18) {
+    } else {
       // ------------------------------------------------ store warps: dY_out image -> next link (and HBM where the residual kernel needs it) -------
-      const int sw = warp - 16;                  // each copies one half (two panels) of the image
-      const uint8_t* src = smem_raw + kOffOut + sw * (kActBytes / 2);
+      // Four warps through the LSU (the TMA unit of a stage CTA only carries loads): per image event (two panels) warp sw moves the
+      // 8 KB half (sw & 1) of panel (sw >> 1).  The buffer is handed back as soon as it has been READ into registers; after the
+      // second event of a group the four warps meet and ONE of them (rotating) publishes the group with a gpu-scope release, whose
+      // fence (it waits for 64 KB of stores to drain at the SM's 27-32 B/clk store path) then stalls each warp only every 4th group.
+      const int sw = warp - 16;
+      const uint8_t* src = smem_raw + kOffOut + (sw >> 1) * kPanelBytes128 + (sw & 1) * kHalfPanel;
       const int gregion = st == 3 ? kGradL7 + 2 : (st == 8 ? kGradL0 : -1);   // dY5 (layer-5 encoding columns) / dY0 (layer 0)
+      long long s_img = 0, s_freed = 0, s_copy = 0, s_fence = 0;
+      const long long s_begin = prof_on ? clock64() : 0;
+      uint32_t ev = 0;
       for (int t = 0; t < n_mine; ++t) {
         const int group = pl + kPipelines * t;
         const int tile = group * 2 + (int)rank;
         const bool tile_ok = tile < p.n_tiles;
         const int ls = t % kLinkSlots, use = t / kLinkSlots;
-        mbar_wait(bar_img_full, (uint32_t)t & 1u);
-        const uint4* sp = reinterpret_cast<const uint4*>(src);
-        if (st < 8) {
-          if (lane == 0) spin_until(flag_freed(st, ls), 2u * (uint32_t)use);
+        for (int ph = 0; ph < 2; ++ph, ++ev) {
+          PIPE_TIMED(s_img, mbar_wait(bar_img_full, ev & 1u));
+          const long long c0 = prof_on ? clock64() : 0;
+          uint4 v[16];   // 32 lanes x 16 x 16 B = 8 KB
+          const uint4* sp = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = sp[i * 32 + lane];
           __syncwarp();
-          uint4* dst = reinterpret_cast<uint4*>(link_base(st, ls) + rank * kActBytes + sw * (kActBytes / 2));
-#pragma unroll 4
-          for (int q = lane; q < (int)(kActBytes / 32); q += 32) dst[q] = sp[q];
+          if (lane == 0) mbar_arrive(bar_img_empty);
+          const size_t img_off = (size_t)(2 * ph + (sw >> 1)) * kPanelBytes128 + (size_t)(sw & 1) * kHalfPanel;
+          if (st < 8) {
+            if (ph == 0) {
+              if (lane == 0) PIPE_TIMED(s_freed, spin_until(flag_freed(st, ls), 2u * (uint32_t)use));
+              __syncwarp();
+            }
+#ifndef NERF_PIPE_EXP_NOSTORE
+            uint4* dst = reinterpret_cast<uint4*>(link_base(st, ls) + rank * kActBytes + img_off);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i * 32 + lane] = v[i];
+#endif
+          }
+          if (gregion >= 0 && tile_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.gstash + grad_region_offset(gregion, n_tiles64) + (uint64_t)tile * kActBytes + img_off);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) __stcs(dst + i * 32 + lane, v[i]);
+          }
+          if (prof_on) s_copy += clock64() - c0;
         }
-        if (gregion >= 0 && tile_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.gstash + grad_region_offset(gregion, n_tiles64) + (uint64_t)tile * kActBytes + sw * (kActBytes / 2));
-#pragma unroll 4
-          for (int q = lane; q < (int)(kActBytes / 32); q += 32) __stcs(dst + q, sp[q]);
+        if (st < 8) {
+          const long long f0 = prof_on ? clock64() : 0;
+          named_bar_sync(4, 128);                       // all four warps' stores of this group are ordered before ...
+          if (sw == (t & 3) && lane == 0) red_release_gpu(flag_ready(st, ls), 1u);   // ... the (cumulative) release of one lane
+          if (prof_on) s_fence += clock64() - f0;
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_img_empty);
-          if (st < 8) red_release_gpu(flag_ready(st, ls), 1u);
-        }
+      }
+      if (prof_on && lane == 0 && rank == 0 && sw == 0) {
+        atomicAdd(p.prof + 9, (unsigned long long)s_img);
+        atomicAdd(p.prof + 10, (unsigned long long)s_freed);
+        atomicAdd(p.prof + 11, (unsigned long long)(s_copy - s_freed));
+        atomicAdd(p.prof + 12, (unsigned long long)(clock64() - s_begin));
+        atomicAdd(p.prof + 24, (unsigned long long)s_fence);
+        atomicAdd(p.prof + 32 + 3 * role + 2, (unsigned long long)(s_copy - s_freed + s_fence));
       }
     }
   }
@@ -717,6 +860,7 @@ extern "C" int nerf_mlp_backward_pipe(float* grads, const float* d_rgbsigma, con
   p.packed = static_cast<const uint8_t*>(packed);
   p.params = params;
   p.inv_scale = 1.f / grad_scale;
+  p.prof = reinterpret_cast<unsigned long long*>(timing_buffer());
   // a pipeline whose consumer waits for a producer needs every pair resident at once: 74 clusters on 148 SMs
   static int clusters_ok[64] = {};
   int dev = 0;

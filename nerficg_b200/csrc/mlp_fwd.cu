@@ -40,6 +40,18 @@
 #include "tc.cuh"
 #include "../../include/nerf_b200.h"
 
+#if defined(NERF_EXP_LSU_STORE) || defined(NERF_EXP_PACED_STORE)
+#define NERF_EXP_STORE_WARPS 1
+#endif
+// operands are handed to the MMA issuer per warp BEFORE the slot's warps meet for the image store / bias refill (measured in round 2:
+// inference 0.689 -> 0.667 ms at 4096 x 192, training unchanged); -DNERF_LATE_HANDOFF restores the round-1 order for A/B timing
+#if !defined(NERF_LATE_HANDOFF) && !defined(NERF_EXP_STORE_WARPS) && !defined(NERF_EXP_EARLY_HANDOFF)
+#define NERF_EXP_EARLY_HANDOFF 1
+#endif
+#ifndef NERF_EXP_PIECE
+#define NERF_EXP_PIECE 8192u
+#endif
+
 namespace nerf {
 using namespace tc;
 
@@ -308,7 +320,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 9, 1ull);
       }
-#if defined(NERF_EXP_LSU_STORE)
+#if defined(NERF_EXP_STORE_WARPS)
     } else if (warp >= 2) {
       // =============================== stash store warps (one per slot) ===============================
       // Measured (tools/l2_probe.py): one SM's TMA engine moves 66 B/clk of bulk loads but only 27-32 B/clk of bulk stores,
@@ -322,6 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
         uint32_t ph = 0;
         (void)act;
+#if defined(NERF_EXP_LSU_STORE)
         auto copy_out = [&](int region, const uint8_t* src, uint32_t bytes, int tile) {
           uint4* dst = reinterpret_cast<uint4*>(p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region));
           const uint4* sp = reinterpret_cast<const uint4*>(src);
@@ -333,6 +346,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             __stcs(dst + q + 32, v1);
           }
         };
+#else
+        // PACED bulk stores: the image leaves in 8 KB pieces and the next piece is only issued when the previous one has been
+        // read out of shared memory, so the TMA unit's queue never holds more than one store piece of this slot and a weight-ring
+        // load queued by the producer warp waits for ~300 cycles of store instead of a whole 64 KB image (~2,200 cycles at the
+        // SM's 27-32 B/clk store path; measured: the issuer's W-full wait tripled in training).
+        const uint64_t pol = l2_evict_first();
+        auto copy_out = [&](int region, const uint8_t* src, uint32_t bytes, int tile) {
+          uint8_t* dst = p.stash + stash_region_offset(region, n_tiles64) + (uint64_t)tile * stash_region_tile_bytes(region);
+          const uint32_t s_addr = smem_base + (uint32_t)(src - smem_raw);
+          if (lane == 0) {
+            for (uint32_t off = 0; off < bytes; off += NERF_EXP_PIECE) {
+              bulk_s2g_hint(dst + off, s_addr + off, NERF_EXP_PIECE, pol);
+              bulk_commit();
+              bulk_wait_read<0>();
+            }
+          }
+          __syncwarp();
+        };
+#endif
         for (int it = 0; it < n_iters; ++it) {
           if (!active(it, slot)) break;
           const int tile = group_of(it, slot) * 2 + (int)rank;
@@ -449,9 +481,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           bulk_commit();
         }
       };
-#if defined(NERF_EXP_LSU_STORE)
+#if defined(NERF_EXP_STORE_WARPS)
       auto stash_store = [&](int region, uint32_t src, uint32_t bytes) {   // event: this warp's part of the image is in shared memory
         if (kTrain && region != kStashDir) {                                 // (DIR leaves together with F: one event)
+          fence_proxy_async_smem();                                          // (bulk stores read the image through the async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_img_full + 8 * slot);
           ++img_events;
@@ -467,7 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       };
 #endif
       // before overwriting a buffer that may still be read by an in-flight bulk store
-#if defined(NERF_EXP_LSU_STORE)
+#if defined(NERF_EXP_STORE_WARPS)
       auto stash_drain = [&]() {   // every event issued so far has been copied out (at most one is outstanding)
         if (kTrain && img_events != img_drained) {
           const long long t0 = prof ? clock64() : 0;
@@ -614,7 +647,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
 #else
         stash_store(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);  // (training) fence + slot barrier + bulk store
         fence_proxy_async_smem();
-#if defined(NERF_EXP_LSU_STORE)
+#if defined(NERF_EXP_STORE_WARPS)
         named_bar_sync(bar_id, kEpiThreadsPerSlot);               // (the event hand-off above has no slot barrier of its own)
 #else
         if (!kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);  // every warp of the slot is done with this stage's bias
@@ -684,7 +717,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         const uint32_t xch = act + 3 * kPanelBytes128 + (uint32_t)row * 16u;
         if (half == 1) st_shared_v4(xch, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(dens));
         stash_store(kStashG, act, 2 * kPanelBytes128);  // (training) its barrier also orders the exchange
-#if defined(NERF_EXP_LSU_STORE)
+#if defined(NERF_EXP_STORE_WARPS)
         if (kTrain) named_bar_sync(bar_id, kEpiThreadsPerSlot);
 #endif
         if (!kTrain) {

@@ -232,6 +232,68 @@ __global__ void __launch_bounds__(512, 1) tmem_read_probe_kernel(unsigned long l
 
 }  // namespace nerf
 
+// ---- tensor-pipe rate probe: `iters` back-to-back cta_group::2 MMAs (M = 256, N = 256, K = 16) on resident operands ------------
+// mode 0: K-major A and B (the chains' flavour); 1: MN-major A and B (weight gradients).  out[0] = cycles from the first issue to the
+// completion barrier.  Answers: do the MN-major MMAs of the fused backward run at the K-major rate (128 cycles each)?
+namespace nerf {
+template <bool kMn>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma2_rate_kernel(unsigned long long* __restrict__ out, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid / 32;
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw + (smem_base - smem_u32(smem_raw)))[i] = 0x3c003c00u;  // fp16 1.0
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(smem_u32(&tmem_base_s), 256);
+    tmem_relinquish2();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  long long t0 = 0;
+  if (rank == 0 && warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(256, 256, kF16, kF16, kMn ? 1 : 0, kMn ? 1 : 0);
+      const uint32_t sa = smem_base, sb = smem_base + 32768;
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        const int ks = i & 3;
+        if (kMn) umma2(tmem, desc_mnmajor(sa, ks, 16384), desc_mnmajor(sb, ks, 16384), idesc, 1);
+        else umma2(tmem, desc_kmajor(sa, ks), desc_kmajor(sb, ks), idesc, 1);
+      }
+      umma_commit2(smem_u32(&bar_done), 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait_cluster(smem_u32(&bar_done), 0);
+  if (rank == 0 && tid == 0) out[0] = (unsigned long long)(clock64() - t0);
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+}  // namespace nerf
+
+extern "C" int nerf_selftest_umma2_rate(unsigned long long* out, int mn_major, int iters, void* stream) {
+  using namespace nerf;
+  NERF_CHECK_ARG(out != nullptr && iters > 0, "selftest_umma2_rate: bad arguments");
+  const int smem = 65536 + 1024;
+  cudaError_t e = mn_major ? cudaFuncSetAttribute(umma2_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : cudaFuncSetAttribute(umma2_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  NERF_CHECK_ARG(e == cudaSuccess, "selftest_umma2_rate: %s", cudaGetErrorString(e));
+  if (mn_major) umma2_rate_kernel<true><<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(out, iters);
+  else umma2_rate_kernel<false><<<2, 128, smem, static_cast<cudaStream_t>(stream)>>>(out, iters);
+  NERF_CHECK_LAUNCH("umma2_rate_kernel");
+  return 0;
+}
+
 static int run_selftest2(float* d_out, const float* a, const float* b, int n, int k, bool mn, void* stream) {
   using namespace nerf;
   NERF_CHECK_ARG(n >= 64 && n <= 256 && n % (mn ? 128 : 64) == 0, "selftest2: n must be a multiple of %d in [64,256], got %d", mn ? 128 : 64, n);
@@ -285,9 +347,10 @@ namespace nerf {
 __global__ void __launch_bounds__(64, 1) l2_stream_kernel(unsigned long long* out, uint8_t* window, uint32_t window_bytes, int mode, int iters) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr int kStages = 8;
-  constexpr uint32_t kChunk = 16384;
-  const uint32_t bars = smem_base + kStages * kChunk;
+  const int csel = (mode >> 4) & 7;                          // chunk size: 0 -> 16 KB (default), else 1 KB << csel (2 KB .. 128 KB ring of 128 KB)
+  const uint32_t kChunk = csel == 0 ? 16384u : (1024u << csel);
+  const int kStages = (int)(131072u / kChunk) < 32 ? (int)(131072u / kChunk) : 32;
+  const uint32_t bars = smem_base + 131072u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) tc::mbar_init(bars + 8 * i, 1);
     tc::fence_barrier_init();
@@ -302,7 +365,7 @@ __global__ void __launch_bounds__(64, 1) l2_stream_kernel(unsigned long long* ou
   for (int i = 0; i < iters; ++i) {
     if (i >= kStages && (mode & 1)) tc::mbar_wait(bars + 8 * stage, phase ^ 1);   // the load that used this stage has landed
     if (mode & 2) {
-      if (i >= kStages) tc::bulk_wait_read<kStages - 1>();
+      if (i >= kStages) tc::bulk_wait_read<7>();
       tc::bulk_s2g(window + (uint64_t)c * kChunk, smem_base + stage * kChunk, kChunk);
       tc::bulk_commit();
     }
@@ -404,7 +467,7 @@ extern "C" int nerf_selftest_l2_stream_lsu(unsigned long long* out, void* window
 extern "C" int nerf_selftest_l2_stream(unsigned long long* out, void* window, uint32_t window_bytes, int mode, int iters, int n_ctas, void* stream) {
   using namespace nerf;
   NERF_CHECK_ARG(out && window && window_bytes >= (1u << 20) && iters > 0 && n_ctas > 0, "selftest_l2_stream: bad arguments");
-  const int smem = 8 * 16384 + 256 + 1024;
+  const int smem = 8 * 16384 + 512 + 1024;
   cudaError_t e = cudaFuncSetAttribute(l2_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   NERF_CHECK_ARG(e == cudaSuccess, "selftest_l2_stream: %s", cudaGetErrorString(e));
   l2_stream_kernel<<<n_ctas, 64, smem, static_cast<cudaStream_t>(stream)>>>(out, static_cast<uint8_t*>(window), window_bytes, mode, iters);

@@ -116,3 +116,29 @@ def test_backward_vs_oracle(ops, net, n_rays, s, scale):
     ops.mlp_backward(grads, up_dev, out, stash, ws, packed['nerf.'], flat['nerf.'], n_rays, s, scale)
     got2 = P.views(grads.cpu())
     assert _rel_l2(got2['feature_layer.weight'], 2 * ref['fp16']['feature_layer.weight']) <= 2e-2
+
+
+@pytest.mark.parametrize('n_rays,s', [(5, 77), (300, 192), (2048, 64)])
+def test_fused_pipeline_backward_matches_two_kernel_path(ops, net, n_rays, s):
+    """The layer-stationary fused backward (csrc/mlp_bwd_pipe.cu, experimental) against the production dgrad + wgrad path on
+    identical stashes: only the fp32 summation order of the weight gradients (and fp32 instead of fp16 dsigma in the density head)
+    differs."""
+    from nerficg_b200 import params as P
+    sd, flat, packed = net
+    g = torch.Generator().manual_seed(11 * n_rays + s)
+    o = (torch.randn(n_rays, 3, generator=g) * 0.3).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1).to(DEV)
+    z = torch.sort(2 + 4 * torch.rand(n_rays, s, generator=g), -1).values.to(DEV)
+    n = n_rays * s
+    stash = torch.empty(ops.mlp_stash_bytes(n), dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(ops.mlp_backward_workspace_bytes(n), dtype=torch.uint8, device=DEV)
+    out = ops.mlp_forward(packed['nerf.'], flat['nerf.'], o, d, d, z, None, stash)
+    up = (torch.randn(n, 4, generator=g) * 1e-3 * 1024).to(DEV)
+    up[:, 3] *= (out.reshape(-1, 4)[:, 3] > 0)
+    g_two, g_pipe = torch.zeros_like(flat['nerf.']), torch.zeros_like(flat['nerf.'])
+    ops.mlp_backward(g_two, up, out, stash, ws, packed['nerf.'], flat['nerf.'], n_rays, s, 1024.0)
+    ops.mlp_backward_pipe(g_pipe, up, out, stash, ws, packed['nerf.'], flat['nerf.'], n_rays, s, 1024.0)
+    torch.cuda.synchronize()
+    for (name, a), b in zip(P.views(g_pipe).items(), P.views(g_two).values()):
+        assert torch.isfinite(a).all(), name
+        assert ((a - b).norm() / (b.norm() + 1e-30)).item() <= 5e-3, name

@@ -23,6 +23,8 @@ for s in $STEPS; do
       timeout 900 python bench.py ${BENCH_ARGS:-} > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err;;
     pipecheck)
       timeout 180 python tools/pipe_check.py > $OUT/pipe_check.txt 2>&1; echo "pipe_check rc=$?" >> $OUT/pipe_check.txt;;
+    pipetiming)
+      timeout 180 python tools/pipe_timing.py > $OUT/pipe_timing.txt 2>&1; echo "rc=$?" >> $OUT/pipe_timing.txt;;
     l2probe)
       timeout 300 python tools/l2_probe.py > $OUT/l2_probe.txt 2>&1;;
     ncuk2)
@@ -36,5 +38,6 @@ done
 tail -3 $OUT/pytest_gpu.log 2>/dev/null
 cat $OUT/l2_probe.txt 2>/dev/null
 cat $OUT/pipe_check.txt 2>/dev/null
+cat $OUT/pipe_timing.txt 2>/dev/null
 grep -h "^---" $OUT/stall_*.txt 2>/dev/null
 head -c 600 $OUT/bench.json 2>/dev/null

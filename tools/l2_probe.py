@@ -25,6 +25,21 @@ for n_ctas in (148, 74, 16):
         ms = a.elapsed_time(b)
         print(f'{n_ctas:4d} CTAs {name:13s}: {nbytes / cyc:7.1f} B/clk/SM  {nbytes * n_ctas / cyc:8.0f} B/clk chip  {nbytes * n_ctas / ms / 1e9:7.2f} TB/s  ({ms:.3f} ms)')
 
+print('--- TMA bulk loads, chunk size sweep (148 CTAs, 128 KB ring per CTA)')
+for csel, kb in ((1, 2), (2, 4), (3, 8), (0, 16), (5, 32), (6, 64)):
+    iters = 4096 * 16 // kb
+    for rep in range(2):
+        out.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.nerf_selftest_l2_stream(out.data_ptr(), win.data_ptr(), win.numel(), 1 | (csel << 4), iters, 148, _lib.stream_ptr()), 'l2_stream')
+        b.record()
+        torch.cuda.synchronize()
+    cyc, nbytes = out.tolist()
+    print(f'  chunk {kb:3d} KB: {nbytes / cyc:7.1f} B/clk/SM   {cyc / iters:7.1f} clk per op')
+import sys
+if '--chunks-only' in sys.argv:
+    sys.exit(0)
 out3 = torch.zeros(4, dtype=torch.int64, device=DEV)
 for n_ctas in (148, 16):
     for n_warps in (2, 4, 8):

@@ -27,7 +27,7 @@ def run(n_rays, s, time_it=False):
     g_old, g_new = torch.zeros_like(flat), torch.zeros_like(flat)
     ops.mlp_backward_legacy(g_old, up, out, stash, ws, packed, flat, n_rays, s, 1024.0)
     torch.cuda.synchronize()
-    ops.mlp_backward(g_new, up, out, stash, ws, packed, flat, n_rays, s, 1024.0)
+    ops.mlp_backward_pipe(g_new, up, out, stash, ws, packed, flat, n_rays, s, 1024.0)
     torch.cuda.synchronize()
     worst = 0.0
     for (name, a), b in zip(params.views(g_new).items(), params.views(g_old).values()):
@@ -37,7 +37,7 @@ def run(n_rays, s, time_it=False):
             print(f'   {name:32s} rel {rel:.3e}  |new| {a.norm().item():.4e} |old| {b.norm().item():.4e}')
     print(f'{n_rays} x {s}: worst per-tensor rel L2 (pipe vs legacy) = {worst:.3e}', flush=True)
     if time_it:
-        for name, fn in (('legacy', ops.mlp_backward_legacy), ('pipe', ops.mlp_backward)):
+        for name, fn in (('legacy', ops.mlp_backward_legacy), ('pipe', ops.mlp_backward_pipe)):
             for _ in range(2):
                 fn(g_new, up, out, stash, ws, packed, flat, n_rays, s, 1024.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

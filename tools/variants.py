@@ -16,6 +16,13 @@ VARIANTS = {
     'nohint': ('NERF_EXP_NOHINT',),              # stores without the L2 evict_first policy
     'earlysplit': ('NERF_EXP_EARLY_HANDOFF', 'NERF_EXP_SPLIT_STORE'),
     'lsu': ('NERF_EXP_LSU_STORE',),              # forward stash images leave through LSU store warps instead of TMA bulk stores
+    'pipe_nored': ('NERF_PIPE_EXP_NORED',),      # fused-backward diagnostics: reducers / epilogue arithmetic / link stores switched off
+    'pipe_noepi': ('NERF_PIPE_EXP_NOEPI',),
+    'pipe_nostore': ('NERF_PIPE_EXP_NOSTORE',),
+    'pipe_none': ('NERF_PIPE_EXP_NORED', 'NERF_PIPE_EXP_NOEPI', 'NERF_PIPE_EXP_NOSTORE'),
+    'paced8': ('NERF_EXP_PACED_STORE',),         # forward stash images leave as paced 8 KB bulk stores issued by one store warp per slot
+    'paced16': ('NERF_EXP_PACED_STORE', 'NERF_EXP_PIECE=16384u'),
+    'paced4': ('NERF_EXP_PACED_STORE', 'NERF_EXP_PIECE=4096u'),
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
