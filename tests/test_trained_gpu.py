@@ -191,13 +191,13 @@ def test_psnr_parity_trained_regime(fw):
 
     def oracle_run(rel_perturbation: float) -> float:
         pg = torch.Generator().manual_seed(99)
+        sd = {}
+        for k, v in sd0.items():
+            w = v.clone()
+            if rel_perturbation > 0 and 'frequency' not in k:
+                w = w * (1.0 + rel_perturbation * torch.randn(w.shape, generator=pg, device='cpu'))
+            sd[k] = w.to(dev).requires_grad_('frequency' not in k)
         with torch.device(dev):
-            sd = {}
-            for k, v in sd0.items():
-                w = v.clone()
-                if rel_perturbation > 0 and 'frequency' not in k:
-                    w = w * (1.0 + rel_perturbation * torch.randn(w.shape, generator=pg))
-                sd[k] = w.to(dev).requires_grad_('frequency' not in k)
             opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1.0)
             for it in range(steps):
                 b = pool[ids[it]]
