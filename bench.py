@@ -29,13 +29,15 @@ N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 
 METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 # algorithmic work: MACs per MLP evaluation
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
+WGRAD_KB_PER_TILE = 1344    # K4b algorithmic bytes: both stashes read once per (layer, operand) job; h7 once since round 2 (density head on the reducer warps)
 KERNELS_PER_STEP = 18       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K8 loss, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~9 torch RNG / memset / copy nodes; the bench loop adds the K0 gather when it assembles a batch)
 N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
 RENDER_VIEWS_PER_RANK = 8   # bounded sample of this rank's shard that is actually rendered and timed (config C)
 SUSTAINED_SECONDS = 5.0     # extra clock-sampled run of the training step (long enough for the power governor to settle)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_mlp_summary.md), keyed like the live table
-NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
+NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': None,   # (re-measured per round: profiles/r02_ncu_mlp_summary.md)
+                    'K4b_mlp_wgrad_fine_r01': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -319,8 +321,9 @@ def run_gpu_arm(args) -> None:
         e_start.record()
         losses = []
         for i in range(args.steps):
-            hb = host[i % len(host)]
-            rb = RayBatch(**{k: v.to(dev, non_blocking=True) for k, v in hb.items()}, _skip_post_init=True)
+            # the public call with HOST buffers: the step copies the pinned fields straight into its static device buffers
+            # (five H2D copies on the step's stream), replays the captured iteration, and the loss is read back
+            rb = RayBatch(**host[i % len(host)], _skip_post_init=True)
             losses.append(trainer.fused_step(rb, camera).item())    # D2H read of the step's loss
         e_end.record()
         sync_all()
@@ -390,8 +393,13 @@ def run_gpu_arm(args) -> None:
 
     # ---- per-kernel roofline (rank 0): live CUDA-event timing of every launch of one iteration ----
     peaks, peak_source = measured_peaks()
-    trainer.fused_step(device_batch(), camera)
-    kt = instrumented_kernel_times(trainer, next(iter(trainer._fused.values())))
+    # (rank 0 alone from here on: nothing below may issue a collective -- the step object is built without running its body)
+    from nerficg_b200.Methods.NeRF.Trainer import _FusedStep
+    probe_step = _FusedStep(trainer, N_RAYS, camera, False)
+    pb = device_batch()
+    probe_step.origin.copy_(pb.origin); probe_step.direction.copy_(pb.direction); probe_step.view_direction.copy_(pb.view_direction)
+    probe_step.rgb_gt.copy_(pb.rgb); probe_step.alpha_gt.copy_(pb.alpha)
+    kt = instrumented_kernel_times(trainer, probe_step)
     evals = {'coarse': N_RAYS * N_COARSE, 'fine': N_RAYS * (N_COARSE + N_FINE)}
     n_tiles = {k: (v + 127) // 128 for k, v in evals.items()}
     table = {}
@@ -402,8 +410,8 @@ def run_gpu_arm(args) -> None:
             row.update(bound='tensor', achieved=FLOP_FWD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
         elif name.startswith('K4a'):
             row.update(bound='tensor', achieved=FLOP_DGRAD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
-        elif name.startswith('K4b'):   # operands re-read from the stashes: 1424 KB per 128-sample tile
-            row.update(bound='hbm', achieved=1424 * 1024 * n_tiles[which] / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
+        elif name.startswith('K4b'):   # operands re-read from the stashes: 1344 KB per 128-sample tile
+            row.update(bound='hbm', achieved=WGRAD_KB_PER_TILE * 1024 * n_tiles[which] / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
                        tensor_tflops=FLOP_WGRAD * evals[which] / ms / 1e9)
         elif name.startswith('K5'):
             s = N_COARSE if which == 'coarse' else N_COARSE + N_FINE

@@ -109,7 +109,11 @@ class NeRFTrainer(BaseTrainer):
         """One full training iteration on ``ray_batch`` (single chunk).  Returns the loss as a device scalar."""
         n = len(ray_batch)
         # everything a captured step freezes is part of the key; at most two steps (each owns a multi-GB stash and a graph) are kept
-        key = (n, float(camera.near_plane), float(camera.far_plane), tuple(float(c) for c in camera.background_color.flatten().tolist()),
+        bg_t = camera.background_color
+        cached = getattr(self, '_camera_key', None)     # (a device-resident background colour must not cost a sync per step)
+        if cached is None or cached[0] is not camera or cached[1] is not bg_t:
+            cached = self._camera_key = (camera, bg_t, tuple(float(c) for c in bg_t.flatten().tolist()))
+        key = (n, float(camera.near_plane), float(camera.far_plane), cached[2],
                float(self.LAMBDA_COLOR_LOSS), float(self.LAMBDA_ALPHA_LOSS), float(self.DENSITY_RANDOM_NOISE_STD), bool(use_graph))
         step = self._fused.get(key)
         if step is None:

@@ -20,7 +20,7 @@ def result():
     world = 2 if n < 4 else 4
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
            '--master-port', '29533', str(ROOT / 'tests' / 'tools' / 'multigpu_worker.py')]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     lines = [l for l in r.stdout.splitlines() if l.startswith('MULTIGPU_RESULT ')]
     assert lines, r.stdout[-3000:] + r.stderr[-6000:]
     res = json.loads(lines[-1][len('MULTIGPU_RESULT '):])

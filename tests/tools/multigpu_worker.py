@@ -83,14 +83,16 @@ def main() -> None:
     cam = ds.default_camera
     bg = cam.background_color.to(dev)
 
+    from nerficg_b200.Methods.NeRF.Loss import NeRFLoss
+    loss_fn = NeRFLoss(1.0, 0.0, True)
+
     def grads_of(model, renderer, sl):
-        trainer = TRAINING_INSTANCE(model=model, renderer=renderer)
-        trainer.FUSED_STEP = False
+        """render_rays -> NeRFLoss -> backward on the rays ids[sl]; NO collective in here (rank 0 also calls it alone)."""
         batch = pool[ids[sl]]
         out = renderer.render_rays(batch, cam, randomize_samples=True, noise=[{'u_c': u_c[sl].contiguous(), 'u_f': u_f[sl].contiguous()}])
-        loss = trainer.loss(out, batch, bg)
+        loss = loss_fn(out, batch, bg)
         loss.backward()
-        return trainer, loss
+        return None, loss
 
     model, renderer = fresh()
     trainer, loss = grads_of(model, renderer, slice(rank * b_per, (rank + 1) * b_per))
