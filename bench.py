@@ -29,15 +29,14 @@ N_TRAIN_VIEWS = 16          # synthetic views resident in HBM (16 x 640k rays x 
 METRIC, UNIT = 'nerf_train_rays_per_s', 'rays/s'
 # algorithmic work: MACs per MLP evaluation
 FLOP_FWD, FLOP_DGRAD, FLOP_WGRAD = 2 * 593408, 2 * 557696, 2 * 593408
-WGRAD_KB_PER_TILE = 1344    # K4b algorithmic bytes: both stashes read once per (layer, operand) job; h7 once since round 2 (density head on the reducer warps)
+WGRAD_KB_PER_TILE = 1424    # K4b algorithmic bytes: both stashes read once per (layer, operand) job
 KERNELS_PER_STEP = 18       # OUR launches per step (ncu launch list, profiles/): pack x2, K1, K2, K3 x2, K5 x2, K8 loss, K6 x2, K4a x2, K4b x2, K7 Adam update x2 + tick (+ ~9 torch RNG / memset / copy nodes; the bench loop adds the K0 gather when it assembles a batch)
 N_TEST_VIEWS = 200          # config C: the test set that is sharded across ranks by view
 RENDER_VIEWS_PER_RANK = 8   # bounded sample of this rank's shard that is actually rendered and timed (config C)
 SUSTAINED_SECONDS = 5.0     # extra clock-sampled run of the training step (long enough for the power governor to settle)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_mlp_summary.md), keyed like the live table
-NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': None,   # (re-measured per round: profiles/r02_ncu_mlp_summary.md)
-                    'K4b_mlp_wgrad_fine_r01': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
+NCU_TRAFFIC_BYTES = {'K4b_mlp_wgrad_fine': 8.944e9 + 0.004e9, 'K3_mlp_fwd_fine': 0.0255e9 + 4.209e9, 'K4a_mlp_dgrad_fine': 0.254e9 + 3.888e9}
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -261,7 +260,9 @@ def run_gpu_arm(args) -> None:
     dev = Framework.config.GLOBAL.DEFAULT_DEVICE
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        torch.distributed.init_process_group('nccl', device_id=dev)
+        import datetime
+        # a mismatched collective must abort the run in two minutes, not in NCCL's default ten
+        torch.distributed.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=120))
     from nerficg_b200.Datasets import RayBatch
     from nerficg_b200.Datasets.Synthetic import SyntheticLegoDataset
     from nerficg_b200.Implementations import Methods
@@ -410,7 +411,7 @@ def run_gpu_arm(args) -> None:
             row.update(bound='tensor', achieved=FLOP_FWD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
         elif name.startswith('K4a'):
             row.update(bound='tensor', achieved=FLOP_DGRAD * evals[which] / ms / 1e9, peak=peaks['bf16_tflops_sustained'], unit='TFLOP/s')
-        elif name.startswith('K4b'):   # operands re-read from the stashes: 1344 KB per 128-sample tile
+        elif name.startswith('K4b'):   # operands re-read from the stashes: 1424 KB per 128-sample tile
             row.update(bound='hbm', achieved=WGRAD_KB_PER_TILE * 1024 * n_tiles[which] / ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
                        tensor_tflops=FLOP_WGRAD * evals[which] / ms / 1e9)
         elif name.startswith('K5'):

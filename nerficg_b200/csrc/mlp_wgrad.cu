@@ -24,7 +24,7 @@ constexpr uint32_t kHalfPanel = 8192;       // 64 rows x 128 B
 constexpr uint32_t kRingBytes = 24 * kHalfPanel;  // 192 KB, carved into as many stages as the job's operands allow
 constexpr uint32_t kOffBars = kRingBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
-constexpr int kNumJobs = 12;
+constexpr int kNumJobs = 13;
 
 struct Seg {
   int16_t buf;        // 0 = gradient stash, 1 = activation stash
@@ -36,11 +36,10 @@ struct Seg {
 struct Job {
   Seg a;              // dY (rows of dW); for head jobs: the activation (columns of the tiny dW^T)
   Seg b[2];           // X segments
-  Seg x;              // extra panel loaded for the reducer warps only (density head: the head-gradient panel), not an MMA operand
   int64_t w_off;      // dW offset in the flat gradient buffer (floats)
   int32_t ld;         // dW row length
   int64_t bias_off;   // bias gradient offset, or -1
-  int32_t head;       // 0 normal; 1 = colour head (dW_c1^T); 3 = normal + density head on the reducer warps (x = head-gradient panel)
+  int32_t head;       // 0 normal; 1 = colour head (dW_c1^T); 2 = density head
   int32_t ctas;       // CTAs assigned to this job
 };
 
@@ -50,31 +49,29 @@ constexpr Seg none() { return Seg{0, 0, 0, 0, 0}; }
 constexpr int gl(int l) { return kGradL7 + (7 - l); }   // gradient-stash region of hidden layer l
 constexpr int hx(int l) { return kStashH0 + l; }        // activation-stash region of h_l
 
-// The density head (dL/dw_sigma[k] = sum_m dsigma_raw[m] h7[m][k], dL/db_sigma = sum_m dsigma_raw[m]) rides on the feature layer's job:
-// its X operand IS h7, so the reducer warps of that job read h7 from the ring stage and the 8 KB head-gradient half panel that
-// is loaded next to it -- round 1 spent a separate job (and a second 64 KB read of h7 per tile) on it: 1,424 -> 1,344 KB per tile.
 __constant__ Job c_jobs[kNumJobs] = {
-    {seg(0, gl(1), 4, 256, 0), {seg(1, hx(0), 4, 256, 0), none()}, none(), L::hidden_w(1), 256, L::hidden_b(1), 0, 13},
-    {seg(0, gl(2), 4, 256, 0), {seg(1, hx(1), 4, 256, 0), none()}, none(), L::hidden_w(2), 256, L::hidden_b(2), 0, 13},
-    {seg(0, gl(3), 4, 256, 0), {seg(1, hx(2), 4, 256, 0), none()}, none(), L::hidden_w(3), 256, L::hidden_b(3), 0, 13},
-    {seg(0, gl(4), 4, 256, 0), {seg(1, hx(3), 4, 256, 0), none()}, none(), L::hidden_w(4), 256, L::hidden_b(4), 0, 13},
-    {seg(0, gl(5), 4, 256, 0), {seg(1, hx(4), 4, 256, 0), none()}, none(), L::kW5, 319, L::kB5, 0, 13},
-    {seg(0, gl(6), 4, 256, 0), {seg(1, hx(5), 4, 256, 0), none()}, none(), L::hidden_w(6), 256, L::hidden_b(6), 0, 13},
-    {seg(0, gl(7), 4, 256, 0), {seg(1, hx(6), 4, 256, 0), none()}, none(), L::hidden_w(7), 256, L::hidden_b(7), 0, 13},
-    {seg(0, kGradF, 4, 256, 0), {seg(1, hx(7), 4, 256, 0), none()}, seg(0, kGradHead, 1, 4, 0), L::kWF, 256, L::kBF, 3, 14},
-    {seg(0, gl(0), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 0), none()}, none(), L::kW0, 63, L::kB0, 0, 10},
-    {seg(0, gl(5), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 256), none()}, none(), L::kW5, 319, -1, 0, 10},
-    {seg(0, kGradC0, 2, 128, 0), {seg(1, kStashF, 4, 256, 0), seg(1, kStashDir, 1, 27, 256)}, none(), L::kWC0, 283, L::kBC0, 0, 15},
-    {seg(1, kStashG, 2, 128, 0), {seg(0, kGradHead, 1, 4, 0), none()}, none(), L::kWC1, 128, L::kBC1, 1, 8},
+    {seg(0, gl(1), 4, 256, 0), {seg(1, hx(0), 4, 256, 0), none()}, L::hidden_w(1), 256, L::hidden_b(1), 0, 13},
+    {seg(0, gl(2), 4, 256, 0), {seg(1, hx(1), 4, 256, 0), none()}, L::hidden_w(2), 256, L::hidden_b(2), 0, 13},
+    {seg(0, gl(3), 4, 256, 0), {seg(1, hx(2), 4, 256, 0), none()}, L::hidden_w(3), 256, L::hidden_b(3), 0, 13},
+    {seg(0, gl(4), 4, 256, 0), {seg(1, hx(3), 4, 256, 0), none()}, L::hidden_w(4), 256, L::hidden_b(4), 0, 13},
+    {seg(0, gl(5), 4, 256, 0), {seg(1, hx(4), 4, 256, 0), none()}, L::kW5, 319, L::kB5, 0, 13},
+    {seg(0, gl(6), 4, 256, 0), {seg(1, hx(5), 4, 256, 0), none()}, L::hidden_w(6), 256, L::hidden_b(6), 0, 13},
+    {seg(0, gl(7), 4, 256, 0), {seg(1, hx(6), 4, 256, 0), none()}, L::hidden_w(7), 256, L::hidden_b(7), 0, 13},
+    {seg(0, kGradF, 4, 256, 0), {seg(1, hx(7), 4, 256, 0), none()}, L::kWF, 256, L::kBF, 0, 13},
+    {seg(0, gl(0), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 0), none()}, L::kW0, 63, L::kB0, 0, 9},
+    {seg(0, gl(5), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 256), none()}, L::kW5, 319, -1, 0, 8},
+    {seg(0, kGradC0, 2, 128, 0), {seg(1, kStashF, 4, 256, 0), seg(1, kStashDir, 1, 27, 256)}, L::kWC0, 283, L::kBC0, 0, 12},
+    {seg(1, kStashG, 2, 128, 0), {seg(0, kGradHead, 1, 4, 0), none()}, L::kWC1, 128, L::kBC1, 1, 6},
+    {seg(1, hx(7), 4, 256, 0), {seg(0, kGradHead, 1, 4, 0), none()}, L::kWS, 256, L::kBS, 2, 9},
 };
 // Residual jobs of the fused backward (mlp_bwd_pipe.cu keeps the eight 256 x 256 layers' gradients on chip): the encoding
 // columns of layers 0 and 5 and the colour head; 320 KB of operands per tile instead of 1,424 KB.  CTAs proportional to bytes.
 constexpr int kNumResidualJobs = 4;
 __constant__ Job c_jobs_res[kNumResidualJobs] = {
-    {seg(0, gl(0), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 0), none()}, none(), L::kW0, 63, L::kB0, 0, 37},
-    {seg(0, gl(5), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 256), none()}, none(), L::kW5, 319, -1, 0, 37},
-    {seg(0, kGradC0, 2, 128, 0), {seg(1, kStashF, 4, 256, 0), seg(1, kStashDir, 1, 27, 256)}, none(), L::kWC0, 283, L::kBC0, 0, 52},
-    {seg(1, kStashG, 2, 128, 0), {seg(0, kGradHead, 1, 4, 0), none()}, none(), L::kWC1, 128, L::kBC1, 1, 22},
+    {seg(0, gl(0), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 0), none()}, L::kW0, 63, L::kB0, 0, 37},
+    {seg(0, gl(5), 4, 256, 0), {seg(1, kStashEnc, 1, 63, 256), none()}, L::kW5, 319, -1, 0, 37},
+    {seg(0, kGradC0, 2, 128, 0), {seg(1, kStashF, 4, 256, 0), seg(1, kStashDir, 1, 27, 256)}, L::kWC0, 283, L::kBC0, 0, 52},
+    {seg(1, kStashG, 2, 128, 0), {seg(0, kGradHead, 1, 4, 0), none()}, L::kWC1, 128, L::kBC1, 1, 22},
 };
 }  // namespace wg
 
@@ -100,7 +97,7 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages, bar_done = bars + 16 * kMaxStages, tmem_slot = bar_done + 8;
   // jobs with small operands (head, encoding) get more, smaller stages: every job keeps ~190 KB of loads in flight,
   // otherwise those CTAs are latency-bound and finish long after the 64 KB-per-stage jobs (measured: SMs 58 % active)
-  const uint32_t kStageBytes = (uint32_t)(job.a.panels + job.b[0].panels + job.b[1].panels + job.x.panels) * kHalfPanel;
+  const uint32_t kStageBytes = (uint32_t)(job.a.panels + job.b[0].panels + job.b[1].panels) * kHalfPanel;
   const int kStages = (int)(kRingBytes / kStageBytes) < kMaxStages ? (int)(kRingBytes / kStageBytes) : kMaxStages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -139,23 +136,23 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
       // per-segment source cursors, computed once: the region tables are runtime loops and one thread issues
       // every copy of this CTA (measured: with the lookups inside the loop the producer was 75 % issue-busy and
       // the kernel ran at 4.3 TB/s; DESIGN.md "K4b")
-      const Seg* segs[4] = {&job.a, &job.b[0], &job.b[1], &job.x};
-      const uint8_t* cur[4];
-      uint32_t tile_stride[4];
-      int panels[4];
-      for (int s = 0; s < 4; ++s) {
+      const Seg* segs[3] = {&job.a, &job.b[0], &job.b[1]};
+      const uint8_t* cur[3];
+      uint32_t tile_stride[3];
+      int panels[3];
+      for (int s = 0; s < 3; ++s) {
         panels[s] = segs[s]->panels;
         cur[s] = region_ptr(*segs[s], tile_lo);
         tile_stride[s] = segs[s]->buf == 0 ? grad_region_tile_bytes(segs[s]->region) : stash_region_tile_bytes(segs[s]->region);
       }
-      const uint32_t stage_bytes = (uint32_t)(na + nb0 + nb1 + job.x.panels) * kHalfPanel;
+      const uint32_t stage_bytes = (uint32_t)(na + nb0 + nb1) * kHalfPanel;
       for (int step = 0; step < n_steps; ++step) {
         const uint32_t half_off = (step & 1) * kHalfPanel;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
         uint32_t dst = smem_base + stage * kStageBytes;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < 3; ++s) {
           const uint8_t* src = cur[s] + half_off;
           for (int pp = 0; pp < panels[s]; ++pp) {
             bulk_g2s_hint(dst, src, kHalfPanel, bar_full + 8 * stage, stream_policy);
@@ -199,10 +196,7 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
   } else if (warp >= 4) {
     // ---- bias reduction: column sums of the dY operand over every half tile ----
     const int t = threadIdx.x - 128;  // 0..127
-    const bool head = job.head == 1;
-    const bool dens = job.head == 3;           // feature-layer job: also reduce the density head from b[0] = h7 and x = head gradients
-    const uint32_t dens_b_off = na * kHalfPanel, dens_x_off = (uint32_t)(na + nb0 + nb1) * kHalfPanel;
-    float d0 = 0.f, d1 = 0.f, dsum = 0.f;
+    const bool head = job.head != 0;
     const int bias_cols = head ? 4 : (job.bias_off >= 0 ? 64 * na : 0);
     const uint32_t bias_seg_off = head ? na * kHalfPanel : 0;  // head jobs: dY is operand B
     float s0 = 0.f, s1 = 0.f;
@@ -219,22 +213,6 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
           const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
           s0 += f.x;
           s1 += f.y;
-        }
-      }
-      if (dens) {   // thread t: input features 2t, 2t + 1 of h7; dsigma_raw = column 3 of the head-gradient panel
-        const uint32_t hb = smem_base + stage * kStageBytes + dens_b_off + ((2 * t) >> 6) * kHalfPanel;
-        const uint32_t xb = smem_base + stage * kStageBytes + dens_x_off;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-          uint32_t w;
-          uint16_t hs;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(hb + panel_offset(r, (2 * t) & 63)));
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hs) : "r"(xb + panel_offset(r, 3)));
-          const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
-          const float ds = __half2float(*reinterpret_cast<__half*>(&hs));
-          d0 = fmaf(ds, f.x, d0);
-          d1 = fmaf(ds, f.y, d1);
-          if (t == 0) dsum += ds;
         }
       }
       named_bar_sync(1, 128);
@@ -255,12 +233,9 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
         } else {
           atomicAdd(grads + job.bias_off + 2, s0 * inv_scale);
         }
+      } else if (t == 1) {  // density head: col 3 -> b_sigma
+        atomicAdd(grads + job.bias_off, s1 * inv_scale);
       }
-    }
-    if (dens) {
-      atomicAdd(grads + L::kWS + 2 * t, d0 * inv_scale);
-      atomicAdd(grads + L::kWS + 2 * t + 1, d1 * inv_scale);
-      if (t == 0) atomicAdd(grads + L::kBS, dsum * inv_scale);
     }
     // ---- flush the accumulated dW block ----
     mbar_wait(bar_done, 0);
@@ -274,8 +249,12 @@ __global__ void __launch_bounds__(wg::kThreads, 1) mlp_wgrad_kernel(float* __res
         uint32_t v[32];
         tmem_ld32(t_row, v);
         tmem_ld_wait();
+        if (job.head == 1) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) atomicAdd(grads + job.w_off + j * 128 + n, __uint_as_float(v[j]) * inv_scale);
+          for (int j = 0; j < 3; ++j) atomicAdd(grads + job.w_off + j * 128 + n, __uint_as_float(v[j]) * inv_scale);
+        } else {
+          atomicAdd(grads + job.w_off + n, __uint_as_float(v[3]) * inv_scale);
+        }
         continue;
       }
       float* wrow = grads + job.w_off + (int64_t)n * job.ld;

@@ -50,6 +50,28 @@ def _worker(rank: int, world: int, port: int, out) -> None:
         w2 = torch.ones(8, requires_grad=True)
         ((x_all @ w2) ** 2).mean().backward()
         ok &= torch.allclose(g_local[0], w2.grad, atol=1e-6)
+        # the captured step's flavour: SUM all-reduce, 1/world folded into the optimiser's gradient read (K7 grad_mult)
+        g_sum = [local[0].clone()]
+        dist.allreduce_sum_(g_sum)
+        ok &= torch.allclose(g_sum[0] * (1.0 / world), grads[0], atol=1e-6)
+        # the NeRF trainer's autograd path under data parallelism: identical start (rank 0's weights), per-rank batches,
+        # all-reduced gradients -> identical weights on every rank after the step (no CUDA kernel involved: CPU Adam on a stand-in loss)
+        from nerficg_b200 import Framework
+        Framework.load_config(None, {'GLOBAL.LOG_LEVEL': 0})
+        from nerficg_b200.Methods.NeRF.Model import NeRF
+        torch.manual_seed(50 + rank)                         # ranks build DIFFERENT weights
+        model = NeRF('ddp').build()
+        dist.broadcast_parameters_([b.flat_params for b in model.blocks()])
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        torch.manual_seed(60 + rank)                         # ... and see different data
+        loss = sum(((p * torch.randn_like(p)).sum()) ** 2 for p in model.parameters())
+        loss.backward()
+        dist.allreduce_mean_([p.grad for p in model.parameters() if p.grad is not None])
+        opt.step()
+        flat = torch.cat([b.flat_params.detach() for b in model.blocks()])
+        both = [torch.empty_like(flat) for _ in range(world)]
+        td.all_gather(both, flat)
+        ok &= torch.equal(both[0], both[1])
         out[rank] = bool(ok)
     finally:
         td.destroy_process_group()

@@ -26,7 +26,8 @@ def main() -> None:
     Framework.setup(None, {'RENDERER.N_SAMPLES': 192, 'RENDERER.COARSE_RATIO': 0.3333333, 'RENDERER.RAY_BATCH_SIZE': 4096,
                            'TRAINING.NUM_ITERATIONS': 1000, 'GLOBAL.LOG_LEVEL': 0}, device_index=local)
     dev = Framework.config.GLOBAL.DEFAULT_DEVICE
-    td.init_process_group('nccl', device_id=dev)
+    import datetime
+    td.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
     from oracle import nerf_oracle as O
     from nerficg_b200.Datasets import RayBatch
     from nerficg_b200.Datasets.Synthetic import SyntheticLegoDataset
