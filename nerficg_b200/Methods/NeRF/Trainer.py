@@ -79,6 +79,9 @@ class NeRFTrainer(BaseTrainer):
         self.model.train()
         self.loss.train()
         dataset.train()
+        if self.sampler_train is None:   # resumed from a '.train' file: the pre-training callbacks do not run again (Base/Trainer.py:234-240)
+            self.init_samplers(_, dataset)
+            dataset.train()
         ray_batch = self.sampler_train.get(dataset=dataset, ray_batch_size=self.BATCH_SIZE)['ray_batch']
         camera = dataset.default_camera
         if self.FUSED_STEP and len(ray_batch) <= self.renderer.RAY_BATCH_SIZE:

@@ -47,3 +47,21 @@ def test_train_and_render_from_blender_files(tmp_path):
     for key in ('rgb', 'alpha', 'depth', 'rgb_coarse', 'alpha_coarse', 'depth_coarse'):
         assert sorted(p.name for p in (out_dir / key).iterdir()) == ['00000.png', '00001.png'], key
     assert (out_dir / 'metrics_8bit.txt').read_text().startswith(trainer.model.model_name)
+    # SSIM next to PSNR in the metrics file; the online-FPS loop of scripts/inference.py -b
+    assert 0.0 < metrics['SSIM'] <= 1.0 and 'SSIM' in (out_dir / 'metrics_8bit.txt').read_text()
+    fps = trainer.renderer.benchmark_fps(dataset.test(), num_iterations=2, output_path=tmp_path / 'performance_6.txt')
+    assert fps['images'] == 4 and fps['fps'] > 0 and 'Average FPS' in (tmp_path / 'performance_6.txt').read_text()
+    # '.train' resume (reference Base/Trainer.py:94-111, Implementations.py:61-62): model, optimiser state and schedule position survive,
+    # and training continues from there through the captured step
+    trainer.save(tmp_path / 'resume.train')
+    resumed = Methods.get_training_instance('NeRF', checkpoint=str(tmp_path / 'resume.train'))
+    assert resumed.model.num_iterations_trained == 6 and resumed.lr_scheduler.last_epoch == 6
+    for (k, a), (_, b) in zip(trainer.model.state_dict().items(), resumed.model.state_dict().items()):
+        assert torch.equal(a, b), k
+    sa, sb = trainer.optimizer.state_dict()['state'], resumed.optimizer.state_dict()['state']
+    assert all(torch.equal(sa[i]['exp_avg'], sb[i]['exp_avg']) and torch.equal(sa[i]['exp_avg_sq'], sb[i]['exp_avg_sq']) for i in sa)
+    resumed.NUM_ITERATIONS = 9
+    resumed.run(dataset)
+    torch.cuda.synchronize()
+    assert resumed.model.num_iterations_trained == 9
+    assert all(bool(torch.isfinite(v).all()) for v in resumed.model.state_dict().values())
