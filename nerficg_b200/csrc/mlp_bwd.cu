@@ -31,6 +31,15 @@ constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 constexpr int kRegsEpilogue = 112, kRegsOther = 32;
+#ifndef NERF_EXP_CPASYNC_MODE
+#define NERF_EXP_CPASYNC_MODE 0
+#endif
+constexpr uint32_t kLsuLag = 2;
+#if defined(NERF_EXP_CPASYNC_W) || defined(NERF_EXP_CPASYNC_W_ALL)
+constexpr bool kLsuW = true;    // weight ring filled by LSU cp.async instead of bulk copies (mlp_fwd.cu)
+#else
+constexpr bool kLsuW = false;
+#endif
 // setmaxnreg moves registers inside the CTA's OWN allocation (launch: 640 threads x 96): what the 128 producer / MMA threads
 // release (96 - 32 each = 8192) must cover what the 512 epilogue threads request (112 - 96 each = 8192), or the
 // increase blocks forever
@@ -99,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) {
-      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_full + 8 * i, (kLsuW && NERF_EXP_CPASYNC_MODE != 2) ? 32 : 1);   // LSU ring (mlp_fwd.cu): one cp.async-completion arrival per producer lane
       mbar_init(bar_w_empty + 8 * i, 1);
       mbar_init(bar_w_peer + 8 * i, 1);
     }
@@ -132,6 +141,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     if (warp == 0) {
       // weight producer: rows [128 * rank, +128) (output columns of dX) of every W^T panel -> one ring stage
       uint32_t stage = 0, phase = 0;
+      uint32_t lsu_issued = 0, lsu_sig = 0;
+      (void)lsu_issued;
+      (void)lsu_sig;
       const uint64_t keep = l2_evict_last();
       long long t_wait = 0;
       const long long t_begin = prof_on ? clock64() : 0;
@@ -142,7 +154,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
             const int first = bwd_first_panel(st), np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
-              if (elect_one()) {
+              if (kLsuW) {
+                const uint8_t* src = wimg + (uint32_t)(first + pp) * kPanelBytes256 + rank * kRingStageBytes + lane * 16;
+                const uint32_t dst = smem_base + kOffRing + stage * kRingStageBytes + lane * 16;
+#if NERF_EXP_CPASYNC_MODE == 1
+#pragma unroll 8
+                for (uint32_t off = 0; off < kRingStageBytes; off += 512) cp_async16(dst + off, src + off);
+#else
+#pragma unroll 8
+                for (uint32_t off = 0; off < kRingStageBytes; off += 512) cp_async16_hint(dst + off, src + off, keep);
+#endif
+#if NERF_EXP_CPASYNC_MODE == 2
+                cp_async_commit();
+                if (++lsu_issued > kLsuLag) {
+                  cp_async_wait<kLsuLag>();
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_w_full + 8 * lsu_sig);
+                  if (++lsu_sig == kRingStages) lsu_sig = 0;
+                }
+#else
+                cp_async_mbar_arrive_noinc(bar_w_full + 8 * stage);
+#endif
+              } else if (elect_one()) {
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, kRingStageBytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes,
                               wimg + (uint32_t)(first + pp) * kPanelBytes256 + rank * kRingStageBytes, kRingStageBytes,
@@ -155,6 +189,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
               }
             }
           }
+#if NERF_EXP_CPASYNC_MODE == 2
+      if (kLsuW) {
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        const uint32_t left = lsu_issued < kLsuLag ? lsu_issued : kLsuLag;
+        for (uint32_t i = 0; i < left; ++i) {
+          if (lane == 0) mbar_arrive(bar_w_full + 8 * lsu_sig);
+          if (++lsu_sig == kRingStages) lsu_sig = 0;
+        }
+      }
+#endif
       if (prof_on && lane == 0) {
         atomicAdd(p.prof + 13, (unsigned long long)t_wait);
         atomicAdd(p.prof + 14, (unsigned long long)(clock64() - t_begin));
@@ -179,6 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
               NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
+              if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t da = make_smem_desc(act + pp * kPanelBytes128, 16u, kAtomBytes);
@@ -211,6 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
             const int np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               mbar_wait(bar_w_full + 8 * stage, phase);
+              if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();
               if (elect_one()) mbar_arrive_cluster(mapa(bar_w_peer + 8 * stage, 0));
               __syncwarp();
               if (++stage == kRingStages) {

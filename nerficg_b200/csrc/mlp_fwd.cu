@@ -48,6 +48,19 @@
 #if !defined(NERF_LATE_HANDOFF) && !defined(NERF_EXP_STORE_WARPS) && !defined(NERF_EXP_EARLY_HANDOFF)
 #define NERF_EXP_EARLY_HANDOFF 1
 #endif
+// -DNERF_EXP_CPASYNC_W: in training the weight ring is filled by LSU cp.async (32 lanes x 16 B) instead of bulk copies, so
+// the loads no longer queue behind 64 KB image stores in the TMA unit; _ALL does it in inference too
+#if defined(NERF_EXP_CPASYNC_W_ALL)
+#define NERF_LSU_W(train) true
+#elif defined(NERF_EXP_CPASYNC_W)
+#define NERF_LSU_W(train) (train)
+#else
+#define NERF_LSU_W(train) false
+#endif
+#ifndef NERF_EXP_CPASYNC_MODE   // 0: L2 hint + cp.async.mbarrier.arrive.noinc; 1: no hint; 2: commit/wait groups + writer-side fence + plain arrive
+#define NERF_EXP_CPASYNC_MODE 0
+#endif
+constexpr uint32_t kLsuLag = 2;
 #ifndef NERF_EXP_PIECE
 #define NERF_EXP_PIECE 8192u
 #endif
@@ -201,9 +214,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
   const uint32_t rank = cluster_ctarank();                // 0 = leader
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool kLsuW = NERF_LSU_W(kTrain);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) {
-      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_full + 8 * i, (kLsuW && NERF_EXP_CPASYNC_MODE != 2) ? 32 : 1);   // LSU ring: one cp.async-completion arrival per producer lane
       mbar_init(bar_w_empty + 8 * i, 1);
       mbar_init(bar_w_peer + 8 * i, 1);
     }
@@ -241,6 +255,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       // one ring stage per K panel: rows [128 * rank, +128) of the 256-neuron panels, [64 * rank, +64) of the
       // 128-neuron colour-layer panels (the cta_group::2 MMA takes the other half from the peer's ring)
       uint32_t stage = 0, phase = 0;
+      uint32_t lsu_issued = 0, lsu_sig = 0;   // (cp.async ring, mode 2) stages issued / next stage to announce
+      (void)lsu_issued;
+      (void)lsu_sig;
       const uint64_t keep = l2_evict_last();
       long long t_wait = 0;
       const long long t_begin = prof_on ? clock64() : 0;
@@ -252,7 +269,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             const uint32_t bytes = st == 9 ? kRingStageBytes / 2 : kRingStageBytes;  // colour layer: 64 of 128 neurons
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
-              if (elect_one()) {
+              if (kLsuW) {
+                const uint8_t* src = p.packed + fwd_panel_offset(first + pp) + rank * bytes + lane * 16;
+                const uint32_t dst = smem_base + kOffRing + stage * kRingStageBytes + lane * 16;
+#if NERF_EXP_CPASYNC_MODE == 1
+#pragma unroll 8
+                for (uint32_t off = 0; off < bytes; off += 512) cp_async16(dst + off, src + off);
+#else
+#pragma unroll 8
+                for (uint32_t off = 0; off < bytes; off += 512) cp_async16_hint(dst + off, src + off, keep);
+#endif
+#if NERF_EXP_CPASYNC_MODE == 2
+                // writer-side completion: the stage issued kLsuLag stages ago has landed -> fence to the async proxy -> one arrival
+                cp_async_commit();
+                if (++lsu_issued > kLsuLag) {
+                  cp_async_wait<kLsuLag>();
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_w_full + 8 * lsu_sig);
+                  if (++lsu_sig == kRingStages) lsu_sig = 0;
+                }
+#else
+                cp_async_mbar_arrive_noinc(bar_w_full + 8 * stage);
+#endif
+              } else if (elect_one()) {
                 mbar_arrive_expect_tx(bar_w_full + 8 * stage, bytes);
                 bulk_g2s_hint(smem_base + kOffRing + stage * kRingStageBytes, p.packed + fwd_panel_offset(first + pp) + rank * bytes, bytes,
                               bar_w_full + 8 * stage, keep);
@@ -266,6 +306,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           }
         }
       }
+#if NERF_EXP_CPASYNC_MODE == 2
+      if (kLsuW) {
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        const uint32_t left = lsu_issued < kLsuLag ? lsu_issued : kLsuLag;
+        for (uint32_t i = 0; i < left; ++i) {
+          if (lane == 0) mbar_arrive(bar_w_full + 8 * lsu_sig);
+          if (++lsu_sig == kRingStages) lsu_sig = 0;
+        }
+      }
+#endif
       if (prof_on && lane == 0) {
         atomicAdd(p.prof + 3, (unsigned long long)t_wait);
         atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
@@ -292,6 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
               NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
+              if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();   // cp.async data arrived through the generic proxy
               tc_fence_after();
               if (elect_one()) {
                 // A: stage 0 reads the encoding panel; panel 4 of stages 5 / 9 is the encoding / direction panel
@@ -400,6 +453,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             const int np = fwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               mbar_wait(bar_w_full + 8 * stage, phase);
+              if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();   // this CTA's half: fenced here, the leader's issuer only sees the relay
               if (elect_one()) mbar_arrive_cluster(mapa(bar_w_peer + 8 * stage, 0));
               __syncwarp();
               if (++stage == kRingStages) {

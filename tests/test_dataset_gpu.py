@@ -48,7 +48,10 @@ def test_train_and_render_from_blender_files(tmp_path):
         assert sorted(p.name for p in (out_dir / key).iterdir()) == ['00000.png', '00001.png'], key
     assert (out_dir / 'metrics_8bit.txt').read_text().startswith(trainer.model.model_name)
     # SSIM next to PSNR in the metrics file; the online-FPS loop of scripts/inference.py -b
-    assert 0.0 < metrics['SSIM'] <= 1.0 and 'SSIM' in (out_dir / 'metrics_8bit.txt').read_text()
+    # (the fixture's 8 x 6 views are smaller than the 11 x 11 SSIM window: after the border crop nothing is left and the mean
+    # is NaN, in torchmetrics as here; the SSIM values themselves are checked against scipy in tests/test_host_logic.py)
+    assert 'SSIM' in (out_dir / 'metrics_8bit.txt').read_text()
+    assert math.isnan(metrics['SSIM']) or 0.0 < metrics['SSIM'] <= 1.0
     fps = trainer.renderer.benchmark_fps(dataset.test(), num_iterations=2, output_path=tmp_path / 'performance_6.txt')
     assert fps['images'] == 4 and fps['fps'] > 0 and 'Average FPS' in (tmp_path / 'performance_6.txt').read_text()
     # '.train' resume (reference Base/Trainer.py:94-111, Implementations.py:61-62): model, optimiser state and schedule position survive,

@@ -15,7 +15,15 @@ for s in $STEPS; do
     variants)
       timeout 300 python tools/kernel_timing.py > $OUT/stall_base.txt 2>&1
       for v in ${VARIANTS:-nostore early split nohint earlysplit}; do
-        NERF_B200_LIB=nerficg_b200/libnerf_b200.$v.so timeout 300 python tools/kernel_timing.py > $OUT/stall_$v.txt 2>&1
+        NERF_B200_LIB=nerficg_b200/libnerf_b200.$v.so timeout 150 python tools/kernel_timing.py > $OUT/stall_$v.txt 2>&1
+      done;;
+    vtests)   # parity tests of the MLP / renderer / trained-regime suites against a variant build
+      for v in ${VARIANTS}; do
+        timeout 600 python tools/with_variant.py nerficg_b200/libnerf_b200.$v.so pytest tests/test_mlp_gpu.py tests/test_renderer_gpu.py tests/test_trained_gpu.py -m gpu -q > $OUT/pytest_$v.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_$v.log
+      done;;
+    vbench)
+      for v in ${VARIANTS}; do
+        timeout 400 python tools/with_variant.py nerficg_b200/libnerf_b200.$v.so bench.py --steps 30 --warmup 5 > $OUT/bench_$v.json 2> $OUT/bench_$v.err; echo "rc=$?" >> $OUT/bench_$v.err
       done;;
     stress)
       timeout 600 python tools/stress_sweep.py > $OUT/stress.txt 2>&1;;
@@ -36,6 +44,8 @@ for s in $STEPS; do
   esac
 done
 tail -3 $OUT/pytest_gpu.log 2>/dev/null
+for f in $OUT/pytest_*.log; do echo $f; tail -2 $f; done 2>/dev/null
+for f in $OUT/bench_*.json; do echo $f; head -c 300 $f; echo; done 2>/dev/null
 cat $OUT/l2_probe.txt 2>/dev/null
 cat $OUT/pipe_check.txt 2>/dev/null
 cat $OUT/pipe_timing.txt 2>/dev/null
