@@ -157,13 +157,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
               if (kLsuW) {
                 const uint8_t* src = wimg + (uint32_t)(first + pp) * kPanelBytes256 + rank * kRingStageBytes + lane * 16;
                 const uint32_t dst = smem_base + kOffRing + stage * kRingStageBytes + lane * 16;
-#if NERF_EXP_CPASYNC_MODE == 1
 #pragma unroll 8
                 for (uint32_t off = 0; off < kRingStageBytes; off += 512) cp_async16(dst + off, src + off);
-#else
-#pragma unroll 8
-                for (uint32_t off = 0; off < kRingStageBytes; off += 512) cp_async16_hint(dst + off, src + off, keep);
-#endif
 #if NERF_EXP_CPASYNC_MODE == 2
                 cp_async_commit();
                 if (++lsu_issued > kLsuLag) {

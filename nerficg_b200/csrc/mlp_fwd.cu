@@ -57,7 +57,7 @@
 #else
 #define NERF_LSU_W(train) false
 #endif
-#ifndef NERF_EXP_CPASYNC_MODE   // 0: L2 hint + cp.async.mbarrier.arrive.noinc; 1: no hint; 2: commit/wait groups + writer-side fence + plain arrive
+#ifndef NERF_EXP_CPASYNC_MODE   // 0: cp.async.mbarrier.arrive.noinc + consumer-side proxy fence; 2: commit/wait groups + writer-side fence + plain arrive
 #define NERF_EXP_CPASYNC_MODE 0
 #endif
 constexpr uint32_t kLsuLag = 2;
@@ -272,13 +272,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
               if (kLsuW) {
                 const uint8_t* src = p.packed + fwd_panel_offset(first + pp) + rank * bytes + lane * 16;
                 const uint32_t dst = smem_base + kOffRing + stage * kRingStageBytes + lane * 16;
-#if NERF_EXP_CPASYNC_MODE == 1
 #pragma unroll 8
                 for (uint32_t off = 0; off < bytes; off += 512) cp_async16(dst + off, src + off);
-#else
-#pragma unroll 8
-                for (uint32_t off = 0; off < bytes; off += 512) cp_async16_hint(dst + off, src + off, keep);
-#endif
 #if NERF_EXP_CPASYNC_MODE == 2
                 // writer-side completion: the stage issued kLsuLag stages ago has landed -> fence to the async proxy -> one arrival
                 cp_async_commit();

@@ -96,16 +96,15 @@ __device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src_smem, uint
 // ---- LSU async copies (non-bulk cp.async): a second global -> shared path that does not queue behind bulk stores in the
 // SM's TMA unit. The data arrives through the generic proxy: consumers that read it through the async proxy (UMMA operand
 // reads) need fence.proxy.async after they have observed the barrier.
-__device__ __forceinline__ void cp_async16_hint(uint32_t dst_smem, const void* src, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy) : "memory");
+// (no L2 cache-hint flavour: `cp.async.cg...L2::cache_hint` with a createpolicy evict_last policy assembles for sm_100a but
+// the resulting LDGSTS raises "illegal instruction" on B200 -- compute-sanitizer, round 2)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 // the barrier receives one arrival from this thread when all of its earlier cp.async have landed (the barrier's expected
 // count must already include it: .noinc)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -24,7 +24,6 @@ VARIANTS = {
     'paced16': ('NERF_EXP_PACED_STORE', 'NERF_EXP_PIECE=16384u'),
     'paced4': ('NERF_EXP_PACED_STORE', 'NERF_EXP_PIECE=4096u'),
     'lsuw': ('NERF_EXP_CPASYNC_W',),             # weight rings of the training forward and dgrad filled by LSU cp.async instead of bulk copies
-    'lsuw1': ('NERF_EXP_CPASYNC_W', 'NERF_EXP_CPASYNC_MODE=1'),   # ... without the L2 cache hint
     'lsuw2': ('NERF_EXP_CPASYNC_W', 'NERF_EXP_CPASYNC_MODE=2'),   # ... commit/wait groups, writer-side proxy fence, plain arrive
     'lsuw_all': ('NERF_EXP_CPASYNC_W_ALL',),     # ... and of the inference forward
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
