@@ -31,6 +31,11 @@ constexpr uint32_t kOffBars = kOffRing + kRingStages * kRingStageBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 constexpr int kRegsEpilogue = 112, kRegsOther = 32;
+#if defined(NERF_NO_SHARE_W)
+constexpr bool kShareW = false;
+#else
+constexpr bool kShareW = true;   // one weight load per stage for both slots (mlp_fwd.cu); every dgrad stage fits the ring
+#endif
 #ifndef NERF_EXP_CPASYNC_MODE
 #define NERF_EXP_CPASYNC_MODE 0
 #endif
@@ -151,6 +156,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (kShareW && slot == 1) continue;   // slot 1 re-uses the panels loaded for slot 0
             const int first = bwd_first_panel(st), np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               NERF_TIMED(prof_on, t_wait, mbar_wait(bar_w_empty + 8 * stage, phase ^ 1));
@@ -208,9 +214,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       long long t_a = 0, t_w = 0;
       const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
-        for (int st = 0; st < kBwdStages; ++st)
+        for (int st = 0; st < kBwdStages; ++st) {
+          const bool both = active(it, 1);
+          const uint32_t stage0 = stage, phase0 = phase;
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (kShareW && slot == 1) {
+              stage = stage0;
+              phase = phase0;
+            }
+            const bool release = !kShareW || slot == 1 || !both;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
             NERF_TIMED(prof_on, t_a, mbar_wait_cluster(bar_a_ready + 8 * slot, a_phase[slot]));
@@ -227,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
                 const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes, 16u, kAtomBytes);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma2(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
-                umma_commit2(bar_w_empty + 8 * stage, 3);
+                if (release) umma_commit2(bar_w_empty + 8 * stage, 3);
                 if (pp == np - 1) umma_commit2(bar_acc_ready + 8 * slot, 3);
               }
               __syncwarp();
@@ -237,6 +250,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
               }
             }
           }
+        }
       if (prof_on && lane == 0) {
         atomicAdd(p.prof + 10, (unsigned long long)t_a);
         atomicAdd(p.prof + 11, (unsigned long long)t_w);
@@ -250,6 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         for (int st = 0; st < kBwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (kShareW && slot == 1) continue;
             const int np = bwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               mbar_wait(bar_w_full + 8 * stage, phase);
@@ -282,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     const uint64_t n_tiles64 = (uint64_t)p.n_tiles;
     const uint32_t a_ready_leader = mapa(bar_a_ready + 8 * slot, 0);
     const bool prof = prof_on && tg == 0 && slot == 0;
-    long long t_accw = 0, t_drain = 0, t_pro = 0, t_pro_compute = 0, t_pro_drain = 0;
+    long long t_accw = 0, t_drain = 0, t_pro = 0, t_pro_compute = 0, t_pro_drain = 0, t_maskw = 0, t_bar = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
@@ -432,6 +447,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         acc_phase ^= 1;
         tc_fence_after();
         gstash_drain();                 // previous image store still reads act
+        if (prof) {   // how long the mask words are still in flight once the accumulator is ready
+          const long long t0 = clock64();
+          asm volatile("mov.b32 %0, %0;" : "+r"(mk4.x));
+          t_maskw += clock64() - t0;
+        }
         const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
         // software pipeline over eight 16-column sub-chunks: the TMEM load of sub-chunk s+1 is in flight while s is processed
         auto run = [&](auto sig_tag) {
@@ -459,7 +479,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(a_ready_leader);
         }
-        named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        NERF_TIMED(prof, t_bar, named_bar_sync(bar_id, kEpiThreadsPerSlot));
         gstash_issue(kGradF + st, act, kActBytes);
 #else
         gstash_store(kGradF + st, act, kActBytes);  // regions: F, L7, L6, ..., L0
@@ -482,6 +502,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       atomicAdd(p.prof + 18, (unsigned long long)t_pro);
       atomicAdd(p.prof + 20, (unsigned long long)t_pro_compute);  // prologue: loads + dL/dg arithmetic
       atomicAdd(p.prof + 21, (unsigned long long)t_pro_drain);    // prologue: wait for the previous tile's last image store
+      atomicAdd(p.prof + 25, (unsigned long long)t_maskw);
+      atomicAdd(p.prof + 26, (unsigned long long)t_bar);
     }
   }
   tc_fence_before();

@@ -57,6 +57,17 @@
 #else
 #define NERF_LSU_W(train) false
 #endif
+// Shared weight stages (default since round 2; -DNERF_NO_SHARE_W restores one load per slot): the two slots of a CTA walk the
+// chain one stage apart, so the weight panels of stage st are needed by slot 0 and, one accumulator later, by slot 1. They are
+// loaded ONCE; slot 1's MMAs release the ring stages (half the L2 -> SM weight stream). Only stages whose panels all fit in the
+// ring can be shared (slot 0 holds them until slot 1 is done): every stage but the two 5-panel ones (skip layer, colour layer).
+// Measured (profiles/r02_chain_kernel_experiments.txt): the issuer's W-full wait halves and its A-ready wait grows by almost
+// as much -- the epilogue is the critical path -- so the gain is 1-2 % (inference 0.674 -> 0.667 ms, training 1.051 -> 1.038).
+#if defined(NERF_NO_SHARE_W)
+#define NERF_SHARE_W(train) false
+#else
+#define NERF_SHARE_W(train) true
+#endif
 #ifndef NERF_EXP_CPASYNC_MODE   // 0: cp.async.mbarrier.arrive.noinc + consumer-side proxy fence; 2: commit/wait groups + writer-side fence + plain arrive
 #define NERF_EXP_CPASYNC_MODE 0
 #endif
@@ -215,6 +226,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool kLsuW = NERF_LSU_W(kTrain);
+  constexpr bool kShareW = NERF_SHARE_W(kTrain);
+  auto shared_stage = [&](int st) { return kShareW && fwd_panels(st) <= kRingStages; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRingStages; ++i) {
       mbar_init(bar_w_full + 8 * i, (kLsuW && NERF_EXP_CPASYNC_MODE != 2) ? 32 : 1);   // LSU ring: one cp.async-completion arrival per producer lane
@@ -265,6 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         for (int st = 0; st < kFwdStages; ++st) {
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (slot == 1 && shared_stage(st)) continue;   // slot 1 re-uses the panels loaded for slot 0
             const int first = fwd_first_panel(st), np = fwd_panels(st);
             const uint32_t bytes = st == 9 ? kRingStageBytes / 2 : kRingStageBytes;  // colour layer: 64 of 128 neurons
             for (int pp = 0; pp < np; ++pp) {
@@ -327,8 +341,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it) {
         for (int st = 0; st < kFwdStages; ++st) {
+          const bool sh = shared_stage(st);
+          const bool both = active(it, 1);
+          const uint32_t stage0 = stage, phase0 = phase;
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (sh && slot == 1) {   // replay the ring stages slot 0 has just used (their barriers are still in the same phase)
+              stage = stage0;
+              phase = phase0;
+            }
+            const bool release = !sh || slot == 1 || !both;
             const uint32_t act = smem_base + slot * kSlotBytes;
             const uint32_t enc = act + kActBytes;
             const uint32_t d_tmem = tmem_base + slot * 256;
@@ -350,7 +372,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   if (ks < ksteps) umma2(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
-                umma_commit2(bar_w_empty + 8 * stage, 3);
+                if (release) umma_commit2(bar_w_empty + 8 * stage, 3);
                 if (pp == np - 1) umma_commit2(bar_acc_ready + 8 * slot, 3);
               }
               __syncwarp();
@@ -445,6 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         for (int st = 0; st < kFwdStages; ++st)
           for (int slot = 0; slot < 2; ++slot) {
             if (!active(it, slot)) continue;
+            if (slot == 1 && shared_stage(st)) continue;
             const int np = fwd_panels(st);
             for (int pp = 0; pp < np; ++pp) {
               mbar_wait(bar_w_full + 8 * stage, phase);
@@ -497,7 +520,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       bulk_g2s(bias_u32, src, bytes, bar_bias + 8 * slot);
     };
     if (tg == 0 && active(0, slot)) bias_fetch(0);
-    long long t_accw = 0, t_drain = 0, t_pro = 0;
+    long long t_accw = 0, t_drain = 0, t_pro = 0, t_bias = 0, t_bar = 0, t_mask = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     for (int it = 0; it < n_iters; ++it) {
@@ -652,7 +675,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           uint32_t va[32], vb[32];
           tmem_ld32(t_acc, va);
           stash_drain();  // the act image of the previous stage may still be being stored
-          mbar_wait(bar_bias + 8 * slot, bias_phase);
+          NERF_TIMED(prof, t_bias, mbar_wait(bar_bias + 8 * slot, bias_phase));
 #pragma unroll
           for (int c = 0; c < 4; c += 2) {
             const uint32_t pbase = act_h + (uint32_t)(c >> 1) * kPanelBytes128;
@@ -690,7 +713,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a_ready_leader);
-        named_bar_sync(bar_id, kEpiThreadsPerSlot);
+        NERF_TIMED(prof, t_bar, named_bar_sync(bar_id, kEpiThreadsPerSlot));
         if (kTrain) stash_issue(st < 8 ? kStashH0 + st : kStashF, act, kActBytes);
         if (tg == 0) bias_fetch(st + 1);
 #else
@@ -710,7 +733,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
         if (kTrain && relu && tile_ok) {
           uint4* md = reinterpret_cast<uint4*>(p.stash + stash_region_offset(kStashMask, n_tiles64) +
                                                (uint64_t)tile * stash_region_tile_bytes(kStashMask) + st * (128 * 32) + row * 32 + half * 16);
+          const long long t0 = prof ? clock64() : 0;
           *md = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          if (prof) t_mask += clock64() - t0;
         }
       }
       // ---------------- stage 9: g = ReLU(acc + b) (128 wide); rgb = sigmoid(W_c1 g + b_c1) on CUDA cores ----------------
@@ -799,6 +824,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
       atomicAdd(p.prof + 6, (unsigned long long)(clock64() - t_begin));
       atomicAdd(p.prof + 7, (unsigned long long)t_drain);
       atomicAdd(p.prof + 8, (unsigned long long)t_pro);
+      atomicAdd(p.prof + 22, (unsigned long long)t_bias);   // (slots 10..21 belong to dgrad) waits the table above counts as busy time
+      atomicAdd(p.prof + 23, (unsigned long long)t_bar);
+      atomicAdd(p.prof + 24, (unsigned long long)t_mask);
     }
   }
   tc_fence_before();

@@ -23,6 +23,9 @@ def report(buf, base, title, ms):
     print(f'--- {title}: {ms:.3f} ms')
     for name, x in zip(NAMES[:9], v[:9]):
         print(f'    {name:26s} {x / n:12.0f} cyc/CTA')
+    if base == 0:   # forward only: waits of one epilogue thread that the table above counts as busy time
+        for name, x in zip(('epilogue wait bias', 'epilogue slot barrier', 'epilogue mask store'), buf[22:25].tolist()):
+            print(f'    {name:26s} {x / n:12.0f} cyc/CTA')
 
 
 def main():
@@ -38,7 +41,7 @@ def main():
     ws = torch.empty(ops.mlp_backward_workspace_bytes(n), dtype=torch.uint8, device=DEV)
     grads = torch.zeros_like(flat)
     up = torch.randn(n, 4, device=DEV) * 1e-3 * 1024
-    buf = torch.zeros(32, dtype=torch.int64, device=DEV)
+    buf = torch.zeros(64, dtype=torch.int64, device=DEV)
 
     def timed(fn):
         for _ in range(2):
@@ -62,6 +65,8 @@ def main():
     v = buf[20:22].tolist()
     n_cta = max(buf[19].item(), 1)
     print(f'    prologue: loads+arithmetic {v[0] / n_cta:12.0f} cyc/CTA, store drain {v[1] / n_cta:12.0f} cyc/CTA')
+    v = buf[25:27].tolist()
+    print(f'    epilogue wait mask words   {v[0] / n_cta:12.0f} cyc/CTA, slot barrier {v[1] / n_cta:12.0f} cyc/CTA')
     for _ in range(3):
         ops.mlp_backward_wgrad(grads, stash, ws, n_rays, s, 1024.0)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

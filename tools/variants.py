@@ -26,6 +26,7 @@ VARIANTS = {
     'lsuw': ('NERF_EXP_CPASYNC_W',),             # weight rings of the training forward and dgrad filled by LSU cp.async instead of bulk copies
     'lsuw2': ('NERF_EXP_CPASYNC_W', 'NERF_EXP_CPASYNC_MODE=2'),   # ... commit/wait groups, writer-side proxy fence, plain arrive
     'lsuw_all': ('NERF_EXP_CPASYNC_W_ALL',),     # ... and of the inference forward
+    'nosharew': ('NERF_NO_SHARE_W',),            # one weight load per slot and stage (the round-1 producer)
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
