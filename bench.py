@@ -510,7 +510,13 @@ def main() -> None:
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile-steps', type=int, default=0, help='run N steps between cudaProfilerStart/Stop and exit (for ncu)')
+    ap.add_argument('--deadline', type=float, default=900.0,
+                    help='seconds after which a run that is still going dumps every thread\'s stack to stderr and exits 1 '
+                         '(a rank stuck in a collective must not hold a multi-GPU box until the caller\'s own limit)')
     args = ap.parse_args()
+    if args.deadline > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.deadline, exit=True)
     if args.impl == 'reference':
         run_reference_arm(args)
     else:
