@@ -36,16 +36,6 @@ constexpr bool kShareW = false;
 #else
 constexpr bool kShareW = true;   // one weight load per stage for both slots (mlp_fwd.cu); every dgrad stage fits the ring
 #endif
-// -DNERF_EXP_SPLIT_N: every stage's MMAs are issued as two N=128 halves (accumulator columns [0,128) then [128,256)) with
-// one accumulator-ready barrier each, so the slot's eight epilogue warps drain half 0 while the tensor pipe computes half 1.
-// A cta_group::2 N=128 instruction takes 64 weight rows from each CTA, so half h covers neurons [64h, 64h+64) (leader's
-// rows) and [128+64h, +64) (peer's rows): accumulator column c of half h belongs to neuron 128 (c / 64) + 64 h + c % 64,
-// i.e. the thread that owns neurons [128 q, +128) reads columns [128 h + 64 q, +64) in pass h -- no image or stash changes.
-#if defined(NERF_EXP_SPLIT_N)
-constexpr int kHalves = 2;
-#else
-constexpr int kHalves = 1;
-#endif
 #ifndef NERF_EXP_CPASYNC_MODE
 #define NERF_EXP_CPASYNC_MODE 0
 #endif
@@ -116,8 +106,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
   const uint32_t bar_w_empty = bars + 8 * kRingStages;
   const uint32_t bar_w_peer = bars + 16 * kRingStages;  // leader only: the peer's half of the ring stage has landed
   const uint32_t bar_a_ready = bars + 24 * kRingStages;  // leader only: both CTAs' operands written
-  const uint32_t bar_acc_ready = bar_a_ready + 16;       // [2 slots][2 halves]
-  const uint32_t tmem_slot = bar_acc_ready + 32;
+  const uint32_t bar_acc_ready = bar_a_ready + 16;
+  const uint32_t tmem_slot = bar_acc_ready + 16;
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the cta_group::2 pair (see mlp_fwd.cu)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,8 +119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_a_ready + 8 * s, 16);  // one arrival per epilogue warp of either CTA
-      mbar_init(bar_acc_ready + 16 * s, 1);
-      mbar_init(bar_acc_ready + 16 * s + 8, 1);
+      mbar_init(bar_acc_ready + 8 * s, 1);
     }
     fence_barrier_init();
   }
@@ -222,7 +211,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
       uint32_t stage = 0, phase = 0;
       uint32_t a_phase[2] = {0, 0};
       constexpr uint32_t idesc = make_idesc(256, 256, kF16, kF16, 0, 0);
-      constexpr uint32_t idesc_half = make_idesc(256, 128, kF16, kF16, 0, 0);
       long long t_a = 0, t_w = 0;
       const long long t_begin = prof_on ? clock64() : 0;
       for (int it = 0; it < n_iters; ++it)
@@ -242,34 +230,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
             a_phase[slot] ^= 1;
             tc_fence_after();
             const int np = bwd_panels(st);
-            const uint32_t sl_stage0 = stage, sl_phase0 = phase;
-            for (int h = 0; h < kHalves; ++h) {
-              if (h) {   // second half: the same ring stages again (still resident: nothing has released them)
-                stage = sl_stage0;
-                phase = sl_phase0;
-              }
-              for (int pp = 0; pp < np; ++pp) {
-                NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
-                NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
-                if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();
-                tc_fence_after();
-                if (elect_one()) {
-                  const uint64_t da = make_smem_desc(act + pp * kPanelBytes128, 16u, kAtomBytes);
-                  // half h: weight rows [64 h, +64) of this CTA's 128 (8 KB into the stage)
-                  const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes + h * (kRingStageBytes / 2), 16u, kAtomBytes);
+            for (int pp = 0; pp < np; ++pp) {
+              NERF_TIMED(prof_on, t_w, mbar_wait(bar_w_full + 8 * stage, phase));
+              NERF_TIMED(prof_on, t_w, mbar_wait_cluster(bar_w_peer + 8 * stage, phase));
+              if (kLsuW && NERF_EXP_CPASYNC_MODE != 2) fence_proxy_async_smem();
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t da = make_smem_desc(act + pp * kPanelBytes128, 16u, kAtomBytes);
+                const uint64_t db = make_smem_desc(smem_base + kOffRing + stage * kRingStageBytes, 16u, kAtomBytes);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma2(d_tmem + 128 * h, da + 2u * ks, db + 2u * ks, kHalves == 2 ? idesc_half : idesc, (pp | ks) != 0);
-                  if (release && h == kHalves - 1) umma_commit2(bar_w_empty + 8 * stage, 3);
-                  if (pp == np - 1) {
-                    umma_commit2(bar_acc_ready + 16 * slot + 8 * h, 3);
-                  }
-                }
-                __syncwarp();
-                if (++stage == kRingStages) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+                for (int ks = 0; ks < 4; ++ks) umma2(d_tmem, da + 2u * ks, db + 2u * ks, idesc, (pp | ks) != 0);
+                if (release) umma_commit2(bar_w_empty + 8 * stage, 3);
+                if (pp == np - 1) umma_commit2(bar_acc_ready + 8 * slot, 3);
+              }
+              __syncwarp();
+              if (++stage == kRingStages) {
+                stage = 0;
+                phase ^= 1;
               }
             }
           }
@@ -466,8 +443,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
         uint4 mk4 = make_uint4(~0u, ~0u, ~0u, ~0u);
         if (st >= 1 && tile_ok)  // ReLU masks of this half of the row (4 words), in flight while the MMAs still run
           mk4 = __ldg(reinterpret_cast<const uint4*>(mask_base + mask_layer * (128 * 32)));
-        NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 16 * slot, acc_phase));
-        if (kHalves == 1) acc_phase ^= 1;
+        NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 8 * slot, acc_phase));
+        acc_phase ^= 1;
         tc_fence_after();
         gstash_drain();                 // previous image store still reads act
         if (prof) {   // how long the mask words are still in flight once the accumulator is ready
@@ -481,33 +458,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
           constexpr bool kSig = decltype(sig_tag)::value;  // dL/dh7 also receives dsigma_raw * w_sigma
           const float* wsp = p.params + L::kWS + 128 * half;
           uint32_t va[16], vb[16];
-          if (kHalves == 2) {
-            // pass h drains accumulator columns [128 h + 64 half, +64) = this thread's neurons [64 h, +64) of its 128 -> act panel
-            // 2 half + h; pass 1 starts when the second N=128 half of the stage's MMAs has completed
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1) {
-                NERF_TIMED(prof, t_accw, mbar_wait(bar_acc_ready + 16 * slot + 8, acc_phase));
-                acc_phase ^= 1;
-                tc_fence_after();
-              }
-              const uint32_t t_half = t_acc - 64 * half + 128 * h;
-              const uint32_t pbase = act_h + (uint32_t)h * kPanelBytes128;
-              tmem_ld16(t_half, va);
-#pragma unroll
-              for (int u = 0; u < 4; u += 2) {
-                const int sg = 4 * h + u;                       // sub-chunk index within the thread's 128 neurons
-                const uint32_t c0 = (uint32_t)u * 32u;          // byte offset of sub-chunk u in the (unswizzled) panel row
-                tmem_ld_wait16(va);
-                tmem_ld16(t_half + 16 * (u + 1), vb);
-                dgrad16<kSig>(va, mk[sg >> 1], 0, wsp + 16 * sg, dsr, pbase + (c0 ^ xr), pbase + ((c0 + 16u) ^ xr));
-                tmem_ld_wait16(vb);
-                if (u + 2 < 4) tmem_ld16(t_half + 16 * (u + 2), va);
-                dgrad16<kSig>(vb, mk[sg >> 1], 8, wsp + 16 * (sg + 1), dsr, pbase + ((c0 + 32u) ^ xr), pbase + ((c0 + 48u) ^ xr));
-              }
-            }
-            return;
-          }
           tmem_ld16(t_acc, va);
 #pragma unroll
           for (int s = 0; s < 8; s += 2) {

@@ -27,7 +27,6 @@ VARIANTS = {
     'lsuw2': ('NERF_EXP_CPASYNC_W', 'NERF_EXP_CPASYNC_MODE=2'),   # ... commit/wait groups, writer-side proxy fence, plain arrive
     'lsuw_all': ('NERF_EXP_CPASYNC_W_ALL',),     # ... and of the inference forward
     'nosharew': ('NERF_NO_SHARE_W',),            # one weight load per slot and stage (the round-1 producer)
-    'splitn': ('NERF_EXP_SPLIT_N',),             # dgrad: two N=128 MMA halves per stage, the epilogue of half 0 overlaps the MMAs of half 1
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
