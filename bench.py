@@ -106,7 +106,7 @@ def cpu_train_step_factory(n_rays: int):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
