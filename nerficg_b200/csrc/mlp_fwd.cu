@@ -157,14 +157,14 @@ __device__ __forceinline__ void write_half_row(uint32_t panel_smem, int row, int
 // these 16 columns (tc.cuh relu_mask_bit layout); accumulates the density head (fp32, weights at ws) when kDens.
 template <bool kDens, bool kMask, int kOff>
 __device__ __forceinline__ uint32_t hidden16(const uint32_t (&v)[32], const float4* __restrict__ b, const float* __restrict__ ws, bool relu,
-                                             uint32_t pbase, uint32_t c0, uint32_t xr, float& dens) {
+                                             uint32_t pbase, uint32_t c0, uint32_t xr, float& dens, const float4* breg = nullptr) {
   uint32_t m = 0;
   uint32_t w[8];
 #pragma unroll
   for (int qq = 0; qq < 4; ++qq) {
     constexpr int kQ0 = kOff / 4;
     const int q = kQ0 + qq;  // index of the 4-column group within the 32-column chunk
-    const float4 bq = b[q];
+    const float4 bq = breg != nullptr ? breg[qq] : b[q];   // (breg: loaded one 16-column group ahead by the caller)
     float x0 = __uint_as_float(v[4 * q + 0]) + bq.x;
     float x1 = __uint_as_float(v[4 * q + 1]) + bq.y;
     float x2 = __uint_as_float(v[4 * q + 2]) + bq.z;
@@ -676,6 +676,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
           tmem_ld32(t_acc, va);
           stash_drain();  // the act image of the previous stage may still be being stored
           NERF_TIMED(prof, t_bias, mbar_wait(bar_bias + 8 * slot, bias_phase));
+#if !defined(NERF_NO_BIAS_AHEAD)
+          // The bias words of 16-column group g + 1 are loaded BEFORE the (asm volatile, "memory") stores of group g: the compiler
+          // cannot move the LDS across them by itself, and ncu's source view showed the first FADD of every group waiting on it
+          // (13 % of the epilogue warps' samples).  Measured (round 2, profiles/r02_chain_kernel_experiments.txt): training
+          // forward 1.049 -> 0.972 ms, inference 0.703 -> 0.695 ms; -DNERF_NO_BIAS_AHEAD restores the in-place loads.
+          float4 ba[4], bb[4];
+          auto load4 = [&](float4 (&dst)[4], int group) {   // group = 16-column group index within this thread's 128 columns
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = bsp[4 * group + i];
+          };
+          load4(ba, 0);
+#pragma unroll
+          for (int c = 0; c < 4; c += 2) {
+            const uint32_t pbase = act_h + (uint32_t)(c >> 1) * kPanelBytes128;
+            tmem_ld_wait32(va);
+            load4(bb, 2 * c + 1);
+            mw[c] = hidden16<kDens, kTrain, 0>(va, bsp, wsp + 32 * c, relu, pbase, 0u, xr, dens, ba);
+            tmem_ld32(t_acc + 32 * (c + 1), vb);
+            load4(ba, 2 * c + 2);
+            mw[c] |= hidden16<kDens, kTrain, 16>(va, bsp, wsp + 32 * c, relu, pbase, 0u, xr, dens, bb);
+            tmem_ld_wait32(vb);
+            load4(bb, 2 * c + 3);
+            mw[c + 1] = hidden16<kDens, kTrain, 0>(vb, bsp, wsp + 32 * (c + 1), relu, pbase, 64u, xr, dens, ba);
+            if (c + 2 < 4) {
+              tmem_ld32(t_acc + 32 * (c + 2), va);
+              load4(ba, 2 * c + 4);
+            }
+            mw[c + 1] |= hidden16<kDens, kTrain, 16>(vb, bsp, wsp + 32 * (c + 1), relu, pbase, 64u, xr, dens, bb);
+          }
+#else
 #pragma unroll
           for (int c = 0; c < 4; c += 2) {
             const uint32_t pbase = act_h + (uint32_t)(c >> 1) * kPanelBytes128;
@@ -688,6 +718,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
             if (c + 2 < 4) tmem_ld32(t_acc + 32 * (c + 2), va);
             mw[c + 1] |= hidden16<kDens, kTrain, 16>(vb, bsp + 8 * (c + 1), wsp + 32 * (c + 1), relu, pbase, 64u, xr, dens);
           }
+#endif
         };
         if (st == 7) run(BoolTag<true>{}); else run(BoolTag<false>{});
         bias_phase ^= 1;

@@ -27,6 +27,7 @@ VARIANTS = {
     'lsuw2': ('NERF_EXP_CPASYNC_W', 'NERF_EXP_CPASYNC_MODE=2'),   # ... commit/wait groups, writer-side proxy fence, plain arrive
     'lsuw_all': ('NERF_EXP_CPASYNC_W_ALL',),     # ... and of the inference forward
     'nosharew': ('NERF_NO_SHARE_W',),            # one weight load per slot and stage (the round-1 producer)
+    'nobiasahead': ('NERF_NO_BIAS_AHEAD',),      # forward: bias words loaded in place (before round 2's one-group-ahead prefetch)
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
