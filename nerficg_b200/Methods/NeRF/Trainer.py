@@ -11,6 +11,8 @@ Two equivalent ways to run an iteration:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ... import Framework, dist, ops, params
@@ -179,8 +181,11 @@ class _FusedStep:
                       for s in ([self.nc, s_tot] if self.nc > 0 else [s_tot])]
         self.ws = torch.empty(ops.mlp_backward_workspace_bytes(n_rays * s_tot), dtype=torch.uint8, device=dev)
         self.packed = [torch.empty(ops.mlp_packed_bytes(), dtype=torch.uint8, device=dev) for _ in self.blocks]
-        # persistent flat gradient buffers; parameter .grad fields are views into them
-        self.grads = [torch.zeros_like(b.flat_params) for b in self.blocks]
+        # persistent flat gradient buffers (slices of ONE allocation, so that both networks can be exchanged in a single
+        # collective); parameter .grad fields are views into them
+        sizes = [b.flat_params.numel() for b in self.blocks]
+        self.grads_all = torch.zeros(sum(sizes), **f32)
+        self.grads = list(torch.split(self.grads_all, sizes))
         if isinstance(trainer.optimizer, FlatAdam):
             trainer.optimizer.bind_flat_grads(self.grads)
         self.scale = default_grad_scale(n_rays)
@@ -190,7 +195,13 @@ class _FusedStep:
             # K7 reads grad * 1/world (the NCCL exchange stays a plain SUM) and clears the buffers behind the read
             trainer.optimizer.grad_mult = 1.0 / self.world
             trainer.optimizer.zero_bound_grads = True
-        self.side_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # how the gradients are exchanged under torch.distributed: 'overlap' = the fine network's all-reduce
+        # on a side stream behind its wgrad + the coarse one at the end; 'merged' = one all-reduce of both networks at the end;
+        # 'none' = no exchange at all (DIAGNOSTIC: the ranks diverge; separates the exchange cost from the max-over-ranks skew)
+        self.exchange = os.environ.get('NERF_B200_DDP_EXCHANGE', 'overlap')
+        if self.exchange not in ('overlap', 'merged', 'none'):
+            raise ValueError(f'NERF_B200_DDP_EXCHANGE={self.exchange!r}: expected overlap, merged or none')
+        self.side_stream = torch.cuda.Stream(device=dev) if self.world > 1 and self.exchange == 'overlap' else None
         self.graph = None
         self.use_graph = use_graph
         self.calls = 0
@@ -236,7 +247,7 @@ class _FusedStep:
                 g.zero_()
         d_rs = ops.composite_backward(z, rs_f, self.direction, self.bg, g_rgb, None, g_alpha, True, self.scale)
         ops.mlp_backward(self.grads[fine], d_rs, rs_f, self.stash[fine], self.ws, self.packed[fine], flats[fine], n, z.shape[1], self.scale)
-        if self.world > 1 and coarse:
+        if self.world > 1 and coarse and self.exchange == 'overlap':
             # the fine network's gradients are reduced over NVLink while the coarse backward runs
             main = torch.cuda.current_stream()
             self.side_stream.wait_stream(main)
@@ -246,11 +257,13 @@ class _FusedStep:
             d_rs_c = ops.composite_backward(z_c, rs_c, self.direction, self.bg, g_rgb_c, None, g_alpha_c, True, self.scale)
             ops.mlp_backward(self.grads[0], d_rs_c, rs_c, self.stash[0], self.ws, self.packed[0], flats[0], n, self.nc, self.scale)
         if self.world > 1:
-            if coarse:
+            if self.exchange == 'none':
+                pass
+            elif self.exchange == 'merged' or not coarse:
+                dist.allreduce_sum_([self.grads_all])
+            else:
                 dist.allreduce_sum_([self.grads[0]])
                 torch.cuda.current_stream().wait_stream(self.side_stream)
-            else:
-                dist.allreduce_sum_(self.grads)
             if not self.flat_adam:
                 for g in self.grads:
                     g.mul_(1.0 / self.world)
