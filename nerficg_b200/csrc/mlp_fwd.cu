@@ -204,7 +204,10 @@ struct BoolTag {
   static constexpr bool value = kV;
 };
 
-template <bool kTrain>
+// kProf: the stall counters (nerf_debug_set_timing) are compiled into their own instantiation; in the production one the
+// compiler drops every clock read and accumulator (with a run-time flag only, ptxas kept the 64-bit accumulators in local
+// memory and their reloads showed up in ncu's hot list)
+template <bool kTrain, bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   using namespace fwd;
   using L = ParamLayout;
@@ -259,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fwd::kThreads, 1) ml
   const int n_iters = ((n_groups + 1) / 2 + n_clusters - 1) / n_clusters;
   auto group_of = [&](int it, int slot) { return (it * n_clusters + cluster_id) * 2 + slot; };
   auto active = [&](int it, int slot) { return group_of(it, slot) < n_groups; };  // identical in both CTAs
-  const bool prof_on = p.prof != nullptr;
+  const bool prof_on = kProf && p.prof != nullptr;
 
   if (warp < 4) {
     setmaxnreg_dec<kRegsOther>();
@@ -907,16 +910,23 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
     cudaGetDevice(&dev__);
     bool& attr_set = attr_set_dev[dev__ & 63];
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
-    cudaError_t e2 = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
-    NERF_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "mlp_forward: cudaFuncSetAttribute failed: %s",
-                   cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    cudaError_t e1 = cudaSuccess;
+    for (auto fn : {(const void*)mlp_fwd_kernel<false, false>, (const void*)mlp_fwd_kernel<true, false>, (const void*)mlp_fwd_kernel<false, true>,
+                    (const void*)mlp_fwd_kernel<true, true>}) {
+      const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd::kSmemBytes);
+      if (e != cudaSuccess) e1 = e;
+    }
+    NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_forward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
     attr_set = true;
   }
-  if (stash != nullptr)
-    mlp_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-  else
-    mlp_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stash != nullptr) {
+    if (p.prof) mlp_fwd_kernel<true, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+    else mlp_fwd_kernel<true, false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+  } else {
+    if (p.prof) mlp_fwd_kernel<false, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+    else mlp_fwd_kernel<false, false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+  }
   NERF_CHECK_LAUNCH("mlp_fwd_kernel");
   return 0;
 }

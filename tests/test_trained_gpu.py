@@ -265,7 +265,11 @@ def test_psnr_parity_trained_regime(fw):
     assert tf['rgb']['p99.9'] <= 1e-3 and tf['rgb']['max'] <= 2e-3, tf
     assert tf['alpha']['p99.9'] <= 1e-3 and tf['alpha']['max'] <= 2e-3, tf
     assert psnr_ref >= 20.0, psnr_ref                     # the trained regime was reached
-    assert all(abs(r - psnr_ref) <= 0.25 for r in runs), (runs, psnr_ref)
+    # single runs, measured over 8 sessions (24 runs): -0.229 .. +0.132 dB around the oracle (sigma 0.09 dB: fp32 atomics in the
+    # weight-gradient reduction make every training a different rounding path)
+    assert all(abs(r - psnr_ref) <= 0.4 for r in runs), (runs, psnr_ref)
     # the north star's 0.05 dB, widened by what the fp32 oracle itself drifts under the perturbations above (first measurement on
     # B200, 1500 steps: CUDA mean 22.95 dB vs oracle 23.04 dB, CUDA runs within +-0.03 dB of each other)
-    assert abs(mean - psnr_ref) <= 0.05 + band, (mean, psnr_ref, psnr_ref_1e6, psnr_ref_5e4)
+    # ... plus twice the standard error of a three-run mean (measured means over 8 sessions: -0.102 .. +0.022 dB)
+    se = (sum((r - mean) ** 2 for r in runs) / (len(runs) - 1)) ** 0.5 / len(runs) ** 0.5
+    assert abs(mean - psnr_ref) <= 0.05 + band + 2.0 * se, (mean, psnr_ref, psnr_ref_1e6, psnr_ref_5e4, se)
