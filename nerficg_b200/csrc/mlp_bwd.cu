@@ -96,7 +96,6 @@ struct BoolTag {
   static constexpr bool value = kV;
 };
 
-template <bool kProf>   // stall counters in their own instantiation (mlp_fwd.cu)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) mlp_dgrad_kernel(const BwdParams p) {
   using namespace bwd;
   using L = ParamLayout;
@@ -141,7 +140,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(bwd::kThreads, 1) ml
   auto active = [&](int it, int slot) { return group_of(it, slot) < n_groups; };
   const uint8_t* wimg = p.packed + kBwdImageOffset;
 
-  const bool prof_on = kProf && p.prof != nullptr;
+  // (the stall counters stay behind this run-time flag here: an instantiation without them -- what mlp_fwd.cu does -- made THIS
+  // kernel 11 % slower, 0.917 -> 1.020 ms, a register-allocation effect measured in round 2)
+  const bool prof_on = p.prof != nullptr;
   if (warp < 4) {
     setmaxnreg_dec<kRegsOther>();
     if (warp == 0) {
@@ -552,16 +553,13 @@ static int run_backward(float* grads, const float* d_rgbsigma, const float* rgbs
     cudaGetDevice(&dev__);
     bool& attr_set = attr_set_dev[dev__ & 63];
     if (!attr_set) {
-      cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
-      cudaError_t e2 = cudaFuncSetAttribute(mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
-      NERF_CHECK_ARG(e1 == cudaSuccess && e2 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s",
-                     cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      cudaError_t e1 = cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd::kSmemBytes);
+      NERF_CHECK_ARG(e1 == cudaSuccess, "mlp_backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1));
       attr_set = true;
     }
     const int group_pairs = ((p.n_tiles + 1) / 2 + 1) / 2;  // one cluster iteration = 2 slots x 2 tiles
     const int grid = 2 * (group_pairs < kNumSMs / 2 ? group_pairs : kNumSMs / 2);
-    if (p.prof) mlp_dgrad_kernel<true><<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-    else mlp_dgrad_kernel<false><<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    mlp_dgrad_kernel<<<grid, bwd::kThreads, bwd::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
     NERF_CHECK_LAUNCH("mlp_dgrad_kernel");
   }
   if (phases & 2) {

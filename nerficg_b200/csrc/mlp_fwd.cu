@@ -920,11 +920,16 @@ extern "C" int nerf_mlp_forward(float* rgbsigma, void* stash, const void* packed
     attr_set = true;
   }
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
+#if defined(NERF_RUNTIME_PROF)   // A/B: always the instantiation that carries the counters behind a run-time flag (the round-1 build)
+  const bool with_prof = true;
+#else
+  const bool with_prof = p.prof != nullptr;
+#endif
   if (stash != nullptr) {
-    if (p.prof) mlp_fwd_kernel<true, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+    if (with_prof) mlp_fwd_kernel<true, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
     else mlp_fwd_kernel<true, false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
   } else {
-    if (p.prof) mlp_fwd_kernel<false, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
+    if (with_prof) mlp_fwd_kernel<false, true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
     else mlp_fwd_kernel<false, false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(p);
   }
   NERF_CHECK_LAUNCH("mlp_fwd_kernel");

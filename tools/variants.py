@@ -28,6 +28,7 @@ VARIANTS = {
     'lsuw_all': ('NERF_EXP_CPASYNC_W_ALL',),     # ... and of the inference forward
     'nosharew': ('NERF_NO_SHARE_W',),            # one weight load per slot and stage (the round-1 producer)
     'nobiasahead': ('NERF_NO_BIAS_AHEAD',),      # forward: bias words loaded in place (before round 2's one-group-ahead prefetch)
+    'runtimeprof': ('NERF_RUNTIME_PROF',),       # forward: always the instantiation with the stall counters behind a run-time flag
     'wrap': ('NERF_EXP_STORE_WRAP',),            # diagnostic: image stores hit a 16-tile window that stays in L2 (no HBM writes)
 }
 
